@@ -1,0 +1,42 @@
+// launch.cuh — per-semantics kernel instantiation units.  Each inst_<sem>.cu includes this with LDPC_INST_SEM defined, so
+// the template instantiations compile in parallel and a semantics mode costs nothing in the others' kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernel_fp.cuh"
+#include "kernel_rp.cuh"
+
+namespace ldpcb200 {
+
+// algo: ldpc_algo_t (2NMS shares the NMS instantiation: only the rescale constants differ). Returns cudaError_t as int.
+typedef int (*fp_launch_fn)(int algo, int et, const FpArgs& args, int blocks, cudaStream_t st);
+typedef int (*rp_launch_fn)(int algo, int et, const RpArgs& args, int blocks, int threads, size_t smem, cudaStream_t st);
+
+int launch_fp_x86(int, int, const FpArgs&, int, cudaStream_t);
+int launch_fp_uniform(int, int, const FpArgs&, int, cudaStream_t);
+int launch_fp_arm(int, int, const FpArgs&, int, cudaStream_t);
+int launch_fp_gpu(int, int, const FpArgs&, int, cudaStream_t);
+int launch_rp_x86(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
+int launch_rp_uniform(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
+int launch_rp_arm(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
+int launch_rp_gpu(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
+
+#ifdef LDPC_INST_SEM
+template <int SEM, int ALGO, bool ET>
+static int do_fp(const FpArgs& a, int blocks, cudaStream_t st)
+{
+    fp_decode_kernel<SEM, ALGO, ET><<<blocks, FP_BLOCK, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+template <int SEM, int ALGO, bool ET>
+static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStream_t st)
+{
+    // per-device attribute, cheap and idempotent: set on every launch so any device of the process is covered
+    cudaError_t e = cudaFuncSetAttribute(rp_decode_kernel<SEM, ALGO, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    rp_decode_kernel<SEM, ALGO, ET><<<blocks, threads, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+#define LDPC_CASE(FN, SEM, ALGO, ...) return et ? FN<SEM, ALGO, true>(__VA_ARGS__) : FN<SEM, ALGO, false>(__VA_ARGS__)
+#endif
+
+}  // namespace ldpcb200

@@ -1,0 +1,499 @@
+// ldpc_b200.cu — the C ABI (include/ldpc_b200.h): handle, kernel selection, stream-slot pipeline, boundary conversions.
+//
+// Replaces the reference's decoder objects: CGPUDecoder + CGPU_Decoder_{MS,OMS,NMS,2NMS}_SIMD::decode
+// (ref: code/gpu_fixed/decoder_template/CGPUDecoder.cpp:14-60, code/gpu_fixed/decoder_oms/CGPU_Decoder_OMS_SIMD.cu:97-149)
+// and the x86 CreateDecoder() products (ref: code/x86/CDecoder/DecoderLibrary.h:44-134).  Where the reference does
+// blocking cudaMemcpy H2D -> Interleaver -> kernel -> InvInterleaver -> blocking D2H on the default stream, decode() here
+// cuts the batch into chunks and runs H2D / decode / D2H of consecutive chunks on rotating stream slots so the three
+// overlap (the pipeline ldpc_multiStream intended: code/ldpc_multiStream/queue/handler.cpp:51-138).
+// There is NO CPU fallback: without a CUDA device every compute entry point returns LDPC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_b200.h"
+#include "boundary.cuh"
+#include "channel.cuh"
+#include "launch.cuh"
+
+using namespace ldpcb200;
+
+namespace {
+
+constexpr int kSlots = 4;
+thread_local std::string g_create_error;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    int8_t* d_llr = nullptr;     size_t llr_bytes = 0;
+    uint8_t* d_hard = nullptr;   size_t hard_bytes = 0;
+    uint8_t* d_iters = nullptr;  size_t iters_bytes = 0;
+    uint32_t* d_V = nullptr;     size_t v_bytes = 0;       // frame-parallel kernel state
+    uint32_t* d_MSG = nullptr;   size_t msg_bytes = 0;
+    int T = 0;                                              // words per variable the V/MSG buffers were laid out for
+};
+
+}  // namespace
+
+struct ldpc_b200_handle_s {
+    int device = 0;
+    ldpc_code_t code{};
+    ldpc_params_t prm{};
+    size_t max_frames = 0, chunk_frames = 0;
+    int kernel = 0;                 // 1 = frame-parallel, 2 = row-parallel on-chip
+    int levels = 0, sms = 0;
+    // row-parallel plan
+    int rp_warps = 0, rp_npad = 0, rp_nsteps = 0; size_t rp_smem = 0;
+    RpStep* d_steps = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
+    uint32_t* d_pos = nullptr;
+    Slot slot[kSlots];
+    bool debug = false;
+    int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_frames_cap = 0, dbg_frames = 0; int dbg_iters = 0;
+    unsigned long long* d_counters = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(ldpc_handle h, int status, const std::string& msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return status;
+}
+
+#define CU_TRY(h, call)                                                                                         \
+    do { cudaError_t e__ = (call);                                                                              \
+         if (e__ != cudaSuccess) return fail(h, LDPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+
+int lo_rail(const ldpc_params_t& p) { return p.semantics == LDPC_SEM_GPU_FIXED ? -128 : -p.sat_var; }
+int hi_rail(const ldpc_params_t& p) { return p.semantics == LDPC_SEM_ARM_SCALAR ? p.sat_var : 127; }
+
+template <typename T>
+int ensure(ldpc_handle h, T** p, size_t* have, size_t need)
+{
+    if (*have >= need) return LDPC_OK;
+    if (*p) { CU_TRY(h, cudaFree(*p)); *p = nullptr; *have = 0; }
+    CU_TRY(h, cudaMalloc((void**)p, need));
+    *have = need;
+    return LDPC_OK;
+}
+
+int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& why)
+{
+    if (p->dtype != LDPC_DTYPE_I8) { why = "only LDPC_DTYPE_I8 is implemented on the GPU in this build"; return LDPC_ERR_UNSUPPORTED; }
+    if (p->schedule != LDPC_SCHED_LAYERED) { why = "only the layered schedule is implemented for fixed point (the reference has no flooding decoder)"; return LDPC_ERR_UNSUPPORTED; }
+    switch (p->semantics) {
+    case LDPC_SEM_X86_SSE: case LDPC_SEM_UNIFORM:
+        if (p->algo != LDPC_ALGO_OMS && p->algo != LDPC_ALGO_NMS) { why = "x86 semantics: OMS or NMS only"; return LDPC_ERR_UNSUPPORTED; }
+        if (p->sat_var != 127) { why = "x86 semantics: sat_var must be 127 (the reference exits otherwise, CDecoder_OMS_fixed_SSE.cpp:114-120)"; return LDPC_ERR_INVALID; }
+        break;
+    case LDPC_SEM_ARM_SCALAR:
+        if (p->algo != LDPC_ALGO_OMS) { why = "ARM scalar semantics: OMS only"; return LDPC_ERR_UNSUPPORTED; }
+        if (p->sat_var < 1 || p->sat_var > 127) { why = "int8 path: 1 <= sat_var <= 127"; return LDPC_ERR_INVALID; }
+        break;
+    case LDPC_SEM_GPU_FIXED: break;
+    default: why = "unknown semantics"; return LDPC_ERR_INVALID;
+    }
+    if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
+    if (p->sat_msg < 1 || p->sat_msg > 127 || p->offset < 0 || p->offset > 127) { why = "sat_msg/offset out of range"; return LDPC_ERR_INVALID; }
+    if (p->factor_q5 < 0 || p->factor_q5 > 255) { why = "factor_q5 must be in [0,255]"; return LDPC_ERR_INVALID; }
+    if (p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS)
+        for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] < 2) { why = "NMS needs row degree >= 2"; return LDPC_ERR_UNSUPPORTED; }
+    if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
+    if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
+    return LDPC_OK;
+}
+
+// Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table.
+int build_rp_plan(ldpc_handle h, std::vector<RpStep>& steps, std::vector<uint16_t>& idx_t, std::vector<uint32_t>& edge_of)
+{
+    const ldpc_code_t& c = h->code;
+    std::vector<int32_t> level(c.n_checks);
+    const int levels = ldpc_b200_level_schedule(&c, level.data());
+    if (levels < 0) return levels;
+    h->levels = levels;
+    std::vector<int> row_deg(c.n_checks), row_cls(c.n_checks); std::vector<uint32_t> row_e0(c.n_checks);
+    { int r = 0; uint32_t e = 0;
+      for (int k = 0; k < c.nb_deg; k++) for (int q = 0; q < c.rows[k]; q++, r++) { row_deg[r] = c.deg[k]; row_cls[r] = k; row_e0[r] = e; e += c.deg[k]; } }
+    std::vector<std::vector<int>> by_level(levels);
+    for (int r = 0; r < c.n_checks; r++) by_level[level[r]].push_back(r);
+    idx_t.assign(c.m, 0); edge_of.assign(c.m, 0);
+    int off = 0;
+    for (int L = 0; L < levels; L++) {
+        bool first = true;
+        for (int k = 0; k < c.nb_deg; k++) {
+            std::vector<int> rows;
+            for (int r : by_level[L]) if (row_cls[r] == k) rows.push_back(r);
+            if (rows.empty()) continue;
+            const int rounds = ((int)rows.size() + 31) / 32;
+            const int per = ((int)rows.size() + rounds - 1) / rounds;
+            for (int q = 0; q < rounds; q++) {
+                const int b = q * per, e = std::min((int)rows.size(), b + per);
+                if (e <= b) continue;
+                RpStep st{}; st.deg = c.deg[k]; st.cls = k; st.nrows = e - b; st.msg_off = off; st.sync = first ? 1 : 0;
+                first = false;
+                for (int z = 0; z < st.nrows; z++)
+                    for (int j = 0; j < st.deg; j++) {
+                        const uint32_t ref_e = row_e0[rows[b + z]] + j;
+                        idx_t[off + j * st.nrows + z] = (uint16_t)c.pos[ref_e];
+                        edge_of[off + j * st.nrows + z] = ref_e;
+                    }
+                off += st.nrows * st.deg;
+                steps.push_back(st);
+            }
+        }
+    }
+    return LDPC_OK;
+}
+
+void destroy_impl(ldpc_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& s : h->slot) {
+        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG);
+    }
+    cudaFree(h->d_steps); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos);
+    cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters);
+    free(h->code.pos);
+    delete h;
+}
+
+size_t hard_row_bytes(ldpc_handle h) { return h->prm.out_format == LDPC_OUT_PACKED ? (size_t)(h->code.n + 7) / 8 : (size_t)h->code.n; }
+
+// decode `frames` frames that are already in device memory, on stream st.  For the frame-parallel kernel the slot's V/MSG
+// state is used, `frames` must fit it.
+int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
+{
+    const ldpc_code_t& c = h->code;
+    const int et = h->prm.early_term == LDPC_ET_SYNDROME;
+    const int lo = lo_rail(h->prm), hi = hi_rail(h->prm);
+    if (h->kernel == 2) {
+        RpArgs a{};
+        a.llr = d_llr; a.hard = d_hard; a.iters_done = d_iters;
+        a.dbg_post = want_debug ? h->d_dbg_post : nullptr; a.dbg_msgs = want_debug ? h->d_dbg_msgs : nullptr;
+        a.idx_t = h->d_idx_t; a.edge_of = h->d_edge_of; a.steps = h->d_steps;
+        a.frames = frames; a.n = c.n; a.m = c.m; a.nsteps = h->rp_nsteps; a.n_pad = h->rp_npad; a.iters = iters;
+        a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.prm = h->prm;
+        const size_t pairs = (frames + 1) / 2;
+        const int blocks = (int)std::min<size_t>((size_t)h->sms, (pairs + h->rp_warps - 1) / h->rp_warps);
+        rp_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_rp_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_rp_uniform
+                        : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_rp_arm : launch_rp_gpu;
+        CU_TRY(h, (cudaError_t)fn(h->prm.algo, et, a, blocks, h->rp_warps * 32, h->rp_smem, st));
+        h->launches += 1;
+        return LDPC_OK;
+    }
+    // frame-parallel: interleave -> decode -> de-interleave + hard decision
+    const int T = (int)(((frames + 3) / 4 + 31) / 32 * 32);
+    int rc;
+    if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
+    if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
+    s.T = T;
+    dim3 tg((unsigned)((frames + 127) / 128), (unsigned)((c.n + 127) / 128));
+    interleave_kernel<<<tg, 256, 0, st>>>(d_llr, s.d_V, frames, c.n, T, lo, hi);
+    CU_TRY(h, cudaGetLastError());
+    FpArgs a{};
+    a.V = s.d_V; a.MSG = s.d_MSG; a.pos = h->d_pos; a.iters_done = nullptr; a.T = T; a.n = c.n; a.m = c.m; a.nb_deg = c.nb_deg;
+    for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { a.deg[i] = c.deg[i]; a.rows[i] = c.rows[i]; }
+    a.iters = iters; a.prm = h->prm;
+    uint8_t* d_it4 = nullptr;
+    if (d_iters) {   // kernel writes 4*T entries (padding frames included) into the slot's scratch, then the valid part is copied
+        if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (size_t)4 * T))) return rc;
+        d_it4 = s.d_iters; a.iters_done = d_it4;
+    }
+    fp_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fp_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fp_uniform
+                    : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fp_arm : launch_fp_gpu;
+    CU_TRY(h, (cudaError_t)fn(h->prm.algo, et, a, (T + FP_BLOCK - 1) / FP_BLOCK, st));
+    if (h->prm.out_format == LDPC_OUT_PACKED) deinterleave_hard_kernel<true><<<tg, 256, 0, st>>>(s.d_V, d_hard, frames, c.n, T, lo);
+    else deinterleave_hard_kernel<false><<<tg, 256, 0, st>>>(s.d_V, d_hard, frames, c.n, T, lo);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 3;
+    if (d_iters && d_iters != d_it4) CU_TRY(h, cudaMemcpyAsync(d_iters, d_it4, frames, cudaMemcpyDeviceToDevice, st));
+    if (want_debug) {
+        fp_debug_state_kernel<<<1024, 256, 0, st>>>(s.d_V, s.d_MSG, h->d_dbg_post, h->d_dbg_msgs, frames, c.n, c.m, T, lo, iters > 0);
+        CU_TRY(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    return LDPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldpc_b200_abi_version(void) { return LDPC_B200_ABI_VERSION; }
+
+int ldpc_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* ldpc_b200_status_string(int s)
+{
+    switch (s) {
+    case LDPC_OK: return "ok";
+    case LDPC_ERR_INVALID: return "invalid argument";
+    case LDPC_ERR_CUDA: return "CUDA error";
+    case LDPC_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case LDPC_ERR_IO: return "code table unreadable or malformed";
+    case LDPC_ERR_NOMEM: return "out of memory";
+    case LDPC_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+    }
+}
+
+void ldpc_b200_default_params(ldpc_params_t* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->algo = LDPC_ALGO_OMS; p->schedule = LDPC_SCHED_LAYERED; p->dtype = LDPC_DTYPE_I8; p->semantics = LDPC_SEM_X86_SSE;
+    p->offset = 1; p->factor_q5 = 29; p->factor1 = 0.75f; p->factor2 = 0.875f;       // (ref: code/x86/main_p.cpp:133-139)
+    p->sat_var = 127; p->sat_msg = 31; p->llr_scale = 8; p->sat_llr = 31;              // (ref: code/x86/main_p.cpp:90-104)
+    p->early_term = LDPC_ET_NONE; p->out_format = LDPC_OUT_BYTES; p->kernel = 0;
+}
+
+const char* ldpc_b200_last_error(ldpc_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_params_t* params, int device, size_t max_frames)
+{
+    if (!out || !code || !params) return fail(nullptr, LDPC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = ldpc_b200_check_code(code);
+    if (rc) return fail(nullptr, rc, "malformed code table");
+    std::string why;
+    if ((rc = validate_params(code, params, why))) return fail(nullptr, rc, why);
+    int ndev = ldpc_b200_device_count();
+    if (ndev <= 0) return fail(nullptr, LDPC_ERR_NO_DEVICE, "no CUDA device visible: the decoder has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, LDPC_ERR_INVALID, "device index out of range");
+    ldpc_handle h = new ldpc_b200_handle_s();
+    h->device = device; h->prm = *params; h->code = *code;
+    h->code.pos = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)code->m);
+    if (!h->code.pos) { delete h; return fail(nullptr, LDPC_ERR_NOMEM, "host allocation failed"); }
+    memcpy(h->code.pos, code->pos, sizeof(uint32_t) * (size_t)code->m);
+    h->max_frames = max_frames ? max_frames : 65536;
+#define CREATE_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__); destroy_impl(h); return fail(nullptr, LDPC_ERR_CUDA, m__); } } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sms = prop.multiProcessorCount;
+    for (auto& s : h->slot) CREATE_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc((void**)&h->d_pos, sizeof(uint32_t) * (size_t)code->m));
+    CREATE_TRY(cudaMemcpy(h->d_pos, code->pos, sizeof(uint32_t) * (size_t)code->m, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc((void**)&h->d_counters, 2 * sizeof(unsigned long long)));
+
+    // kernel selection: the on-chip row-parallel kernel needs the whole state of >= 8 frame pairs per SM in shared memory
+    std::vector<RpStep> steps; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of;
+    h->kernel = 1;
+    if (code->n <= 65535 && params->kernel != 1) {
+        if ((rc = build_rp_plan(h, steps, idx_t, edge_of))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
+        h->rp_npad = (code->n + 3) / 4 * 4;
+        const int m_pad = (code->m + 3) / 4 * 4;
+        const size_t fixed = steps.size() * sizeof(RpStep) + (((size_t)code->m * 2 + 15) / 16) * 16;
+        const size_t per_warp = (size_t)(h->rp_npad + m_pad) * 4;
+        const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
+        int warps = budget > fixed ? (int)((budget - fixed) / per_warp) : 0;
+        warps = std::min(warps, RP_MAX_THREADS / 32);
+        const int min_warps = params->kernel == 2 ? 1 : 8;
+        if (warps >= min_warps) {
+            h->kernel = 2; h->rp_warps = warps; h->rp_nsteps = (int)steps.size(); h->rp_smem = fixed + per_warp * warps;
+            CREATE_TRY(cudaMalloc((void**)&h->d_steps, steps.size() * sizeof(RpStep)));
+            CREATE_TRY(cudaMemcpy(h->d_steps, steps.data(), steps.size() * sizeof(RpStep), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_idx_t, idx_t.size() * sizeof(uint16_t)));
+            CREATE_TRY(cudaMemcpy(h->d_idx_t, idx_t.data(), idx_t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_edge_of, edge_of.size() * sizeof(uint32_t)));
+            CREATE_TRY(cudaMemcpy(h->d_edge_of, edge_of.data(), edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the row-parallel kernel"); }
+    } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 65535"); }
+    if (h->kernel == 1 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
+#undef CREATE_TRY
+    // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
+    size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_warps * 2 : (size_t)h->sms * 512 * 4;
+    h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, std::max<size_t>(h->max_frames / 4, 2 * wave)), 1);
+    *out = h;
+    return LDPC_OK;
+}
+
+void ldpc_b200_destroy(ldpc_handle h) { destroy_impl(h); }
+
+int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
+{
+    if (!h || !value) return LDPC_ERR_INVALID;
+    switch (what) {
+    case LDPC_INFO_KERNEL: *value = h->kernel; break;
+    case LDPC_INFO_LEVELS: *value = h->levels; break;
+    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : 16384; break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_warps * 2 : FP_BLOCK * 4; break;
+    case LDPC_INFO_LAUNCHES: *value = h->launches; break;
+    case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
+    case LDPC_INFO_DEVICE: *value = h->device; break;
+    default: return fail(h, LDPC_ERR_INVALID, "unknown info key");
+    }
+    return LDPC_OK;
+}
+
+int ldpc_b200_set_debug(ldpc_handle h, int enable) { if (!h) return LDPC_ERR_INVALID; h->debug = enable != 0; return LDPC_OK; }
+
+int ldpc_b200_host_alloc(void** p, size_t bytes)
+{
+    if (!p) return LDPC_ERR_INVALID;
+    if (ldpc_b200_device_count() <= 0) return LDPC_ERR_NO_DEVICE;
+    return cudaMallocHost(p, bytes) == cudaSuccess ? LDPC_OK : LDPC_ERR_NOMEM;
+}
+int ldpc_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LDPC_OK : LDPC_ERR_CUDA; }
+
+int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters_done, void* cuda_stream)
+{
+    if (!h || !d_llr || !d_hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode_device: bad argument");
+    if (frames == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
+    const bool dbg = h->debug;
+    if (dbg) {
+        int rc; size_t have_p = h->dbg_frames_cap * h->code.n, have_m = h->dbg_frames_cap * (size_t)h->code.m;
+        if ((rc = ensure(h, &h->d_dbg_post, &have_p, frames * h->code.n))) return rc;
+        if ((rc = ensure(h, &h->d_dbg_msgs, &have_m, frames * (size_t)h->code.m))) return rc;
+        h->dbg_frames_cap = std::max(h->dbg_frames_cap, frames); h->dbg_frames = frames; h->dbg_iters = iters;
+    }
+    return launch_decode(h, h->slot[0], (const int8_t*)d_llr, d_hard, frames, iters, d_iters_done, st, dbg);
+}
+
+int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* hard, size_t frames, int iters, uint8_t* iters_done)
+{
+    if (!h || slot < 0 || slot >= kSlots || !llr || !hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode_async: bad argument");
+    if (frames == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    Slot& s = h->slot[slot];
+    const size_t n = h->code.n, hb = hard_row_bytes(h);
+    int rc;
+    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * n))) return rc;
+    if ((rc = ensure(h, &s.d_hard, &s.hard_bytes, frames * hb))) return rc;
+    uint8_t* d_it = nullptr;
+    if (iters_done) {
+        if (h->kernel == 2) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
+        else { const size_t T = ((frames + 3) / 4 + 31) / 32 * 32; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
+    }
+    CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n, cudaMemcpyHostToDevice, s.stream));
+    const bool dbg = h->debug && slot == 0;
+    if (dbg) {
+        size_t have_p = h->dbg_frames_cap * n, have_m = h->dbg_frames_cap * (size_t)h->code.m;
+        if ((rc = ensure(h, &h->d_dbg_post, &have_p, frames * n))) return rc;
+        if ((rc = ensure(h, &h->d_dbg_msgs, &have_m, frames * (size_t)h->code.m))) return rc;
+        h->dbg_frames_cap = std::max(h->dbg_frames_cap, frames); h->dbg_frames = frames; h->dbg_iters = iters;
+    }
+    if ((rc = launch_decode(h, s, s.d_llr, s.d_hard, frames, iters, d_it, s.stream, dbg))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(hard, s.d_hard, frames * hb, cudaMemcpyDeviceToHost, s.stream));
+    if (iters_done) CU_TRY(h, cudaMemcpyAsync(iters_done, d_it, frames, cudaMemcpyDeviceToHost, s.stream));
+    return LDPC_OK;
+}
+
+int ldpc_b200_sync(ldpc_handle h, int slot)
+{
+    if (!h || slot < -1 || slot >= kSlots) return fail(h, LDPC_ERR_INVALID, "sync: bad slot");
+    CU_TRY(h, cudaSetDevice(h->device));
+    for (int i = 0; i < kSlots; i++) if (slot < 0 || slot == i) CU_TRY(h, cudaStreamSynchronize(h->slot[i].stream));
+    return LDPC_OK;
+}
+
+int ldpc_b200_decode(ldpc_handle h, const void* llr, uint8_t* hard, size_t frames, int iters, uint8_t* iters_done)
+{
+    if (!h || !llr || !hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode: bad argument");
+    const size_t n = h->code.n, hb = hard_row_bytes(h);
+    const size_t chunk = (h->debug) ? std::max<size_t>(frames, 1) : h->chunk_frames;   // debug: one chunk so the state is whole
+    int rc = LDPC_OK, k = 0;
+    for (size_t f = 0; f < frames && rc == LDPC_OK; f += chunk, k++) {
+        const size_t cnt = std::min(chunk, frames - f);
+        const int slot = h->debug ? 0 : (k % kSlots);
+        if (k >= kSlots) CU_TRY(h, cudaStreamSynchronize(h->slot[slot].stream));   // slot buffers are reused
+        rc = ldpc_b200_decode_async(h, slot, (const int8_t*)llr + f * n, hard + f * hb, cnt, iters, iters_done ? iters_done + f : nullptr);
+    }
+    int rc2 = ldpc_b200_sync(h, -1);
+    return rc ? rc : rc2;
+}
+
+int ldpc_b200_debug_state(ldpc_handle h, void* posteriors, void* msgs, size_t frames)
+{
+    if (!h) return LDPC_ERR_INVALID;
+    if (!h->debug || !h->d_dbg_post || frames > h->dbg_frames) return fail(h, LDPC_ERR_INVALID, "debug_state: enable ldpc_b200_set_debug and decode first (frames <= last decode)");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaDeviceSynchronize());
+    if (posteriors) CU_TRY(h, cudaMemcpy(posteriors, h->d_dbg_post, frames * h->code.n, cudaMemcpyDeviceToHost));
+    if (msgs) CU_TRY(h, cudaMemcpy(msgs, h->d_dbg_msgs, frames * (size_t)h->code.m, cudaMemcpyDeviceToHost));
+    return LDPC_OK;
+}
+
+int ldpc_b200_quantize(ldpc_handle h, const float* y, int8_t* q, size_t count)
+{
+    if (!h || !y || !q) return fail(h, LDPC_ERR_INVALID, "quantize: bad argument");
+    if (count == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    float* d_y = nullptr; int8_t* d_q = nullptr;
+    CU_TRY(h, cudaMalloc((void**)&d_y, count * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&d_q, count);
+    if (e != cudaSuccess) { cudaFree(d_y); return fail(h, LDPC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaStream_t st = h->slot[0].stream;
+    cudaMemcpyAsync(d_y, y, count * sizeof(float), cudaMemcpyHostToDevice, st);
+    quantize_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 65535), 256, 0, st>>>(d_y, d_q, count, (float)h->prm.llr_scale, h->prm.sat_llr);
+    cudaMemcpyAsync(q, d_q, count, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cudaFree(d_y); cudaFree(d_q);
+    h->launches += 1;
+    if (e != cudaSuccess) return fail(h, LDPC_ERR_CUDA, cudaGetErrorString(e));
+    return LDPC_OK;
+}
+
+int ldpc_b200_awgn_device(ldpc_handle h, void* d_llr, size_t frames, float sigma, uint64_t seed, uint64_t first_frame, void* cuda_stream)
+{
+    if (!h || !d_llr) return fail(h, LDPC_ERR_INVALID, "awgn_device: bad argument");
+    if (frames == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
+    const size_t total = frames * (size_t)((h->code.n + 3) / 4);
+    awgn_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 1u << 20), 256, 0, st>>>((int8_t*)d_llr, frames, h->code.n, sigma, seed, first_frame,
+                                                                                         (float)h->prm.llr_scale, h->prm.sat_llr);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return LDPC_OK;
+}
+
+int ldpc_b200_awgn(ldpc_handle h, void* llr_host, size_t frames, float sigma, uint64_t seed, uint64_t first_frame)
+{
+    if (!h || !llr_host) return fail(h, LDPC_ERR_INVALID, "awgn: bad argument");
+    if (frames == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    int rc;
+    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * (size_t)h->code.n))) return rc;
+    if ((rc = ldpc_b200_awgn_device(h, s.d_llr, frames, sigma, seed, first_frame, s.stream))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(llr_host, s.d_llr, frames * (size_t)h->code.n, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(h, cudaStreamSynchronize(s.stream));
+    return LDPC_OK;
+}
+
+int ldpc_b200_count_errors_device(ldpc_handle h, const uint8_t* d_hard, size_t frames, uint64_t* out2_host, void* cuda_stream)
+{
+    if (!h || !d_hard || !out2_host) return fail(h, LDPC_ERR_INVALID, "count_errors_device: bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
+    CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    if (frames) {
+        count_errors_kernel<<<(unsigned)std::min<size_t>((frames + 7) / 8, 4096), 256, 0, st>>>(d_hard, frames, h->code.n, h->code.n - h->code.n_checks,
+                                                                                               h->prm.out_format == LDPC_OUT_PACKED, h->d_counters);
+        CU_TRY(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    unsigned long long r[2];
+    CU_TRY(h, cudaMemcpyAsync(r, h->d_counters, sizeof(r), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    out2_host[0] = r[0]; out2_host[1] = r[1];
+    return LDPC_OK;
+}
+
+}  // extern "C"

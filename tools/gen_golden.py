@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Mint known-answer fixtures from the REFERENCE's own decoders (oracle/_ref, built from /root/reference by oracle/Makefile).
+
+The reference ships no golden vectors, so the fixtures under tests/golden/ are outputs of its decoders run here:
+  K1/K2/K3  576x288  x86 SSE binary: OMS offset 1/2, NMS factor 29/24, I in {1,2,5,10}, AWGN @2 dB + saturating stress inputs
+  K4        16 frames each of 1944x972, 2048x384, 2304x1152, 4000x2000, 64800x32400, I=10 (posteriors/messages as SHA-256 for the big ones)
+  K5        ARM-tree scalar decoder with the stop criterion: per-frame iteration counts, I_max in {10,30}, 1..3 dB
+Run in the container that has /root/reference; the GPU box and CI only read the .npz files.
+"""
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+from _helpers import Code, awgn_llr, stress_llr, ref_x86, ref_x86_decode, ref_arm, ref_arm_decode  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    OUT.mkdir(exist_ok=True)
+    code = Code.load("576x288")
+    L = ref_x86("576x288")
+    assert L is not None, "build oracle/_ref first (make -C oracle)"
+    llr = np.concatenate([awgn_llr(code, 48, 2.0, 101), stress_llr(code, 32, 102), stress_llr(code, 16, 103, full_range=True)])
+    out = {"llr": llr}
+    for algo, param in [("OMS", 1), ("OMS", 2), ("NMS", 29), ("NMS", 24)]:
+        for iters in [1, 2, 5, 10]:
+            r = ref_x86_decode(L, algo, param, llr, iters)
+            key = f"{algo}_{param}_{iters}"
+            out[key + "_hard"] = np.packbits(r["hard"], axis=1, bitorder="little")
+            if iters in (1, 10):
+                out[key + "_post"] = r["post"]; out[key + "_msgs"] = r["msgs"]
+            else:
+                out[key + "_sha"] = np.array([sha(r["post"]), sha(r["msgs"])])
+    np.savez_compressed(OUT / "k123_576x288_x86sse.npz", **out)
+
+    for name in ["1944x972", "2048x384", "2304x1152", "4000x2000", "64800x32400"]:
+        c = Code.load(name)
+        Lc = ref_x86(name)
+        llr = np.concatenate([awgn_llr(c, 12, 2.0, 200 + c.n % 97), stress_llr(c, 4, 300 + c.n % 89)])
+        out = {"llr": llr}
+        algos = [("OMS", 1)] + ([("NMS", 29)] if len(c.deg) <= 2 else [])
+        for algo, param in algos:
+            r = ref_x86_decode(Lc, algo, param, llr, 10)
+            key = f"{algo}_{param}_10"
+            out[key + "_hard"] = np.packbits(r["hard"], axis=1, bitorder="little")
+            out[key + "_sha"] = np.array([sha(r["post"]), sha(r["msgs"])])
+        np.savez_compressed(OUT / f"k4_{name}_x86sse.npz", **out)
+
+    La = ref_arm("576x288")
+    llr = np.concatenate([awgn_llr(code, 24, 1.0, 401), awgn_llr(code, 24, 2.0, 402), awgn_llr(code, 24, 3.0, 403), stress_llr(code, 8, 404)])
+    out = {"llr": llr}
+    for (off, sv, sm) in [(1, 127, 31), (1, 63, 15)]:
+        for imax in [10, 30]:
+            r = ref_arm_decode(La, code, off, sv, sm, True, llr, imax)
+            key = f"ET_{off}_{sv}_{sm}_{imax}"
+            out[key + "_hard"] = np.packbits(r["hard"], axis=1, bitorder="little")
+            out[key + "_iters"] = r["iters"]
+            out[key + "_post"] = r["post"].astype(np.int8); out[key + "_msgs"] = r["msgs"].astype(np.int8)
+    np.savez_compressed(OUT / "k5_576x288_armscalar_et.npz", **out)
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
