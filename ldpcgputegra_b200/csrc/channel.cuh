@@ -14,12 +14,19 @@
 
 namespace ldpcb200 {
 
+// (int)x as the reference's x86 build computes it: truncation toward zero, and the "integer indefinite" INT_MIN for NaN or
+// |x| >= 2^31 (cvttss2si), so that even absurd inputs quantise like the reference (to -sat).
+__device__ __forceinline__ int quantize_one(float p, int sat)
+{
+    int v = (fabsf(p) < 2147483648.0f) ? __float2int_rz(p) : (int)0x80000000;
+    v = max(v, -sat);
+    return min(v, sat);
+}
+
 __global__ void quantize_kernel(const float* __restrict__ y, int8_t* __restrict__ q, size_t count, float scale, int sat)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-        int v = __float2int_rz(__fmul_rn(scale, y[i]));
-        v = max(v, -sat); v = min(v, sat);
-        q[i] = (int8_t)v;
+        q[i] = (int8_t)quantize_one(__fmul_rn(scale, y[i]), sat);
     }
 }
 
@@ -59,9 +66,7 @@ __global__ void awgn_kernel(int8_t* __restrict__ q, size_t frames, int n, float 
         for (int b = 0; b < 4; b++) {
             if (p + b < n) {
                 const float y = -1.0f + sigma * g[b];
-                int v = __float2int_rz(__fmul_rn(scale, y));
-                v = max(v, -sat); v = min(v, sat);
-                q[f * (size_t)n + p + b] = (int8_t)v;
+                q[f * (size_t)n + p + b] = (int8_t)quantize_one(__fmul_rn(scale, y), sat);
             }
         }
     }

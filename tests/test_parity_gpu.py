@@ -187,7 +187,9 @@ def test_device_resident_path_and_counters(code576):
     dec = pkg.CGPUDecoder(code576, nb_frames=F)
     d_llr = torch.empty((F, code576.n), dtype=torch.int8, device="cuda")
     d_hard = torch.empty((F, code576.n), dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    st = ts.cuda_stream
     dec.awgn_device(d_llr.data_ptr(), F, pkg.sigma_for(2.0, 0.5), 77, 0, st)
     dec.decode_device(d_llr.data_ptr(), d_hard.data_ptr(), F, 10, stream=st)
     be, fe = dec.count_errors_device(d_hard.data_ptr(), F, st)
