@@ -206,10 +206,11 @@ def main():
     torch.cuda.synchronize()
 
     # ---- value: device-resident, kernel only ----
+    sampler = ClockSampler(local_rank)           # NVML is initialised BEFORE the warm-up so no idle gap precedes the timed region
+    barrier()
     for i in range(warmup):
         dec.decode_device(d_llr[i % NBUF].data_ptr(), d_hard.data_ptr(), F, ITERS, stream=stream)
-    barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.start()
     l0 = dec.info(pkg.INFO_LAUNCHES)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

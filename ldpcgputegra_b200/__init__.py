@@ -187,6 +187,9 @@ def default_params(**kw) -> ParamsT:
             v = ALGO[v]
         if k == "semantics" and isinstance(v, str):
             v = SEM[v]
+        if k == "group":          # (G warps, P pairs) experiment knob of the on-chip kernel
+            p.reserved[0], p.reserved[1] = v
+            continue
         setattr(p, k, v)
     return p
 

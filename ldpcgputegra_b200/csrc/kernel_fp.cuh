@@ -59,7 +59,7 @@ __device__ __forceinline__ void fp_row(const FpArgs& A, int t, size_t e, const R
             xu[j] = __hmin2(__hfma2_sat(wU, inv256, nM), K.top);               // clamp(v - m) in the biased domain
             a[j] = pass1_edge<SEM, ALGO, Q>(s, xu[j], K);
         }
-        RowOut o; row_finish<SEM, ALGO>(s, D, K, o);
+        RowOut o; row_finish<SEM, ALGO>(s, D, K, K.msg_c, o);
 #pragma unroll
         for (int j = 0; j < D; j++) {
             h2 msg, unew;
@@ -98,7 +98,7 @@ __device__ __noinline__ void fp_row_generic(const FpArgs& A, int t, size_t e, in
             pass1_edge<SEM, ALGO, Q>(s[g], xu, K);
         }
     }
-    RowOut o[2]; row_finish<SEM, ALGO>(s[0], D, K, o[0]); row_finish<SEM, ALGO>(s[1], D, K, o[1]);
+    RowOut o[2]; row_finish<SEM, ALGO>(s[0], D, K, K.msg_c, o[0]); row_finish<SEM, ALGO>(s[1], D, K, K.msg_c, o[1]);
     for (int j = 0; j < D; j++) {
         const size_t vi = (size_t)__ldg(A.pos + e + j) * A.T + t;
         const uint32_t wv = A.V[vi];

@@ -1,32 +1,41 @@
 // kernel_rp.cuh — "row-parallel" on-chip decoder for codes whose whole state fits in shared memory.
 //
-// One WARP owns one frame PAIR (the two halves of every __half2) for all iterations; nothing but LLR-in and bits-out
-// touches HBM (the reference keeps posteriors AND messages in global memory and re-reads them every iteration:
-// code/gpu_fixed/decoder_oms/cuda/CUDA_OMS_SIMD.cu:160-187).  Lanes are rows: the layered schedule in reference row order
-// is cut into LEVELS of mutually independent rows (ldpc_b200_level_schedule), so running a level's rows
-// concurrently and the levels in order gives bit-identical results to the sequential reference loop
+// A GROUP of G warps owns P frame PAIRS (the two halves of every __half2) for all iterations; nothing but LLR-in and
+// bits-out touches HBM (the reference keeps posteriors AND messages in global memory and re-reads them every iteration:
+// code/gpu_fixed/decoder_oms/cuda/CUDA_OMS_SIMD.cu:160-187).  Lanes are (pair, row) tasks: the layered schedule in reference
+// row order is cut into LEVELS of mutually independent rows (ldpc_b200_level_schedule), so running a level's
+// rows concurrently and the levels in order is bit-identical to the sequential reference loop
 // (ref: code/x86/CDecoder/OMS/CDecoder_OMS_fixed_SSE.cpp:156-554).  A level is executed in "steps" of <= 32 rows of one
-// degree; only a __syncwarp separates levels.
+// degree; the P*nrows tasks of a step are spread over the G*32 lanes of the group (576x288: 4 pairs x 24 rows = 3 full
+// warps), and only a named barrier over the group's G warps (a __syncwarp when G = 1) separates levels.
 //
-// Shared memory per CTA:  idx[M] u16 (step-transposed edge table) | steps | per warp: U[n] h2 (biased posteriors),
-// MS[M] h2 (messages, step-transposed: edge j of the row on lane z of a step lives at msg_off + j*nrows + z so that both
-// the u16 index loads and the message accesses of a warp are conflict-free).
-// Roofline: SM issue / shared-memory pipe; HBM traffic = N + N (or N/8) bytes per frame, once.
+// Shared memory per CTA:  steps | idx[] u16 (step-transposed byte offsets into U) | flags | per pair: U[n] h2 (biased
+// posteriors), MS[] h2 (messages, step-transposed: edge j of row z of a step lives at msg_off + j*stride + z, so the index
+// loads and the message accesses of a warp are conflict-free and, for the specialised (degree, stride) variants, every
+// per-edge address is an immediate offset).
+// Roofline: SM issue slots; HBM traffic = N bytes in + N (or N/8) bytes out per frame, once.
 #pragma once
 #include "rowops.cuh"
 
 namespace ldpcb200 {
 
 #define RP_MAX_THREADS 768
+#define RP_MAX_GROUPS 15          // named barriers 1..15
 
-struct RpStep {
-    int32_t deg;        // degree of every row of this step
-    int32_t cls;        // degree class (0 = first) — selects the X86_SSE quirk / GPU first-iteration clamp
-    int32_t nrows;      // rows (= active lanes) in this step, <= 32
-    int32_t msg_off;    // offset of this step's block in idx[] / MS[]
-    int32_t sync;       // 1 = a new level starts here: __syncwarp before
-    int32_t pad[3];
+struct RpStep {         // read by the kernel as one 128-bit load (first four words) — keep the field order
+    uint16_t deg;       // degree of every row of this step
+    uint16_t nrows;     // rows in this step (<= 32)
+    uint16_t stride;    // element stride between consecutive edges of a row in idx[] / MS[] (>= nrows)
+    uint8_t cls;        // degree class (0 = first): selects the X86_SSE quirk / the GPU first-iteration clamp
+    uint8_t sync;       // 1 = a new level starts here: group barrier before
+    uint32_t msg_off;   // element offset of this step's block in idx[] / MS[]
+    uint32_t magic;     // ceil(65536 / nrows): task -> (pair, row) without a division
+    uint32_t variant;   // 0 = generic (run-time degree/stride) ; 1.. = specialised (degree, stride) instantiation
+    uint32_t pad[3];    // 32 bytes: keeps every later shared-memory region 16-byte aligned
 };
+static_assert(sizeof(RpStep) == 32, "RpStep must stay 32 bytes");
+
+struct RpRun { int32_t first, count, variant, quirk; };
 
 struct RpArgs {
     const int8_t* llr;        // [frames][n] frame-major
@@ -34,126 +43,180 @@ struct RpArgs {
     uint8_t* iters_done;      // nullable [frames]
     int8_t* dbg_post;         // nullable [frames][n]
     int8_t* dbg_msgs;         // nullable [frames][m]   (reference edge order)
-    const uint16_t* idx_t;    // [m]  step-transposed variable indices
-    const uint32_t* edge_of;  // [m]  step-transposed -> reference edge number (debug only)
+    const uint16_t* idx_t;    // [m_elems]  step-transposed byte offsets (4*variable)
+    const uint32_t* edge_of;  // [m_elems]  step-transposed -> reference edge number, 0xFFFFFFFF for padding (debug only)
     const RpStep* steps;
+    const RpRun* runs;       // [nruns] consecutive steps sharing one instantiation
     size_t frames;
-    int n, m, nsteps, n_pad;  // n_pad: U row length in words
+    int n, m, nsteps, nruns;
+    int pair_words;           // words per pair in shared memory (n_pad + m_elems + bank-spreading pad)
+    int n_pad;                // U length in words (multiple of 4)
+    int m_elems;              // padded message elements per pair (multiple of 4)
+    int G, P;                 // warps per group, pairs per full group
+    int groups;               // groups per CTA
+    int slots;                // pair slots per CTA (the last group may own fewer than P)
     int iters;
     int packed;
     ldpc_params_t prm;
 };
 
-template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
-__device__ __forceinline__ void rp_row(h2* __restrict__ U, h2* __restrict__ MS, const uint16_t* __restrict__ idx, int a0, int stride,
-                                       const RowConsts& K, uint32_t keep)
+__device__ __forceinline__ void group_sync(int G, int bar_id)
 {
-    int vi[D];
+    if (G == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(G * 32) : "memory");
+}
+
+// Shared memory is addressed through 32-bit shared-window offsets and explicit ld/st.shared in the hot loop: generic 64-bit
+// pointers cost 3-4 extra integer instructions per access (first profile: profiles/r01_ncu_rp_v2_g11.txt, 36.7 warp
+// instructions per edge against 21 in the row body itself).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// ---- one row, degree and stride known at compile time: every per-edge address is base + immediate --------------------
+// ub = shared address of the pair's U, msa = shared address of MS[msg_off + z], ixa = shared address of idx[msg_off + z]
+template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void rp_row(uint32_t ub, uint32_t msa, uint32_t ixa, const RowConsts& K, h2 msg_c, uint32_t keep)
+{
+    uint32_t ua[D], f[D];
     h2 xu[D], a[D], mo[D], uo[D];
-    RowState s; row_begin(s, K);
 #pragma unroll
-    for (int j = 0; j < D; j++) vi[j] = idx[a0 + j * stride];
+    for (int j = 0; j < D; j++) ua[j] = ub + lds_u16(ixa + 2 * NR * j);
 #pragma unroll
-    for (int j = 0; j < D; j++) uo[j] = U[vi[j]];
+    for (int j = 0; j < D; j++) uo[j] = bits_h2(lds_u32(ua[j]));
     if (!FIRST) {
 #pragma unroll
-        for (int j = 0; j < D; j++) mo[j] = MS[a0 + j * stride];
+        for (int j = 0; j < D; j++) mo[j] = bits_h2(lds_u32(msa + 4 * NR * j));
     }
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-        xu[j] = FIRST ? uo[j] : __hmin2(__hadd2_sat(uo[j], __hneg2(mo[j])), K.top);   // FIRST: m = 0 and U is already inside the rails
-        a[j] = pass1_edge<SEM, ALGO, Q>(s, xu[j], K);
-    }
-    RowOut o; row_finish<SEM, ALGO>(s, D, K, o);
+    for (int j = 0; j < D; j++) xu[j] = FIRST ? uo[j] : __hmin2(__hadd2_sat(uo[j], __hneg2(mo[j])), K.top);   // FIRST: m = 0, U already inside the rails
+    RowState s;
+    row_pass1<SEM, ALGO, Q, D>(xu, a, f, s, K);
+    RowOut o; row_finish<SEM, ALGO>(s, D, K, msg_c, o);
 #pragma unroll
     for (int j = 0; j < D; j++) {
         h2 msg, unew;
-        pass2_edge<SEM>(xu[j], a[j], o, K, msg, unew);
+        pass2_edge_f(xu[j], a[j], f[j], o, K, msg, unew);
         if (ET) {   // frozen frame (keep = 0xFFFF in its half) retains posterior and message
             unew = bits_h2((h2_bits(uo[j]) & keep) | (h2_bits(unew) & ~keep));
             if (!FIRST) msg = bits_h2((h2_bits(mo[j]) & keep) | (h2_bits(msg) & ~keep));
         }
-        U[vi[j]] = unew;
-        MS[a0 + j * stride] = msg;
+        sts_u32(ua[j], h2_bits(unew));
+        sts_u32(msa + 4 * NR * j, h2_bits(msg));
     }
 }
 
-// run-time degree (> 8): two passes, contributions recomputed in pass 2
+// ---- run-time degree / stride: two passes, contributions recomputed in pass 2 ------------------------------------------
 template <int SEM, int ALGO, bool FIRST, bool ET, bool Q>
-__device__ __noinline__ void rp_row_generic(h2* __restrict__ U, h2* __restrict__ MS, const uint16_t* __restrict__ idx, int a0, int stride, int D,
-                                            const RowConsts& K, uint32_t keep)
+__device__ __noinline__ void rp_row_generic(uint32_t ub, uint32_t msa, uint32_t ixa, int D, int stride, const RowConsts& K, h2 msg_c, uint32_t keep)
 {
     RowState s; row_begin(s, K);
     for (int j = 0; j < D; j++) {
-        h2 u = U[idx[a0 + j * stride]];
-        h2 xu = FIRST ? u : __hmin2(__hadd2_sat(u, __hneg2(MS[a0 + j * stride])), K.top);
+        const h2 u = bits_h2(lds_u32(ub + lds_u16(ixa + 2 * stride * j)));
+        const h2 xu = FIRST ? u : __hmin2(__hadd2_sat(u, __hneg2(bits_h2(lds_u32(msa + 4 * stride * j)))), K.top);
         pass1_edge<SEM, ALGO, Q>(s, xu, K);
     }
-    RowOut o; row_finish<SEM, ALGO>(s, D, K, o);
+    RowOut o; row_finish<SEM, ALGO>(s, D, K, msg_c, o);
     for (int j = 0; j < D; j++) {
-        const int vi = idx[a0 + j * stride];
-        h2 u = U[vi], mold = FIRST ? h2_const(0.0f) : MS[a0 + j * stride];
-        h2 xu = FIRST ? u : __hmin2(__hadd2_sat(u, __hneg2(mold)), K.top);
-        h2 a = magnitude<SEM, ALGO, Q>(signed_contrib(xu, K), K);
+        const uint32_t ua = ub + lds_u16(ixa + 2 * stride * j);
+        const h2 u = bits_h2(lds_u32(ua)), mold = FIRST ? h2_const(0.0f) : bits_h2(lds_u32(msa + 4 * stride * j));
+        const h2 xu = FIRST ? u : __hmin2(__hadd2_sat(u, __hneg2(mold)), K.top);
+        const h2 a = magnitude<SEM, ALGO, Q>(signed_contrib(xu, K), K);
         h2 msg, unew;
         pass2_edge<SEM>(xu, a, o, K, msg, unew);
         if (ET) {
             unew = bits_h2((h2_bits(u) & keep) | (h2_bits(unew) & ~keep));
             if (!FIRST) msg = bits_h2((h2_bits(mold) & keep) | (h2_bits(msg) & ~keep));
         }
-        U[vi] = unew;
-        MS[a0 + j * stride] = msg;
+        sts_u32(ua, h2_bits(unew));
+        sts_u32(msa + 4 * stride * j, h2_bits(msg));
+    }
+}
+
+// specialised variants: id = 1 + (deg - 6) * 2 + (stride == 32)  for deg in {6,7,8}, stride in {24,32}
+__host__ __device__ __forceinline__ int rp_variant_id(int deg, int stride)
+{
+    if (deg < 6 || deg > 8 || (stride != 24 && stride != 32)) return 0;
+    return 1 + (deg - 6) * 2 + (stride == 32 ? 1 : 0);
+}
+
+// everything the step loop needs, in registers: shared-window addresses and group geometry
+struct RpCtx {
+    uint32_t steps_s, idx_s, flags_s, state_s;   // shared addresses: step table, index table, this group's flags, this group's pairs
+    uint32_t pair_bytes, ms_off;                 // bytes per pair; byte offset of MS inside a pair (= 4 * n_pad)
+    int gl, GT, G, bar;                          // lane index in the group, lanes in the group, warps in the group, barrier id
+};
+
+// one run = consecutive steps that share the instantiation (degree, stride, quirk class)
+template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void rp_run(const RpCtx& c, int first, int count, int valid_pairs, const RowConsts& K)
+{
+    for (int s = first; s < first + count; s++) {
+        const uint4 sd = lds_u128(c.steps_s + 32u * s);         // {deg | nrows<<16, stride | cls<<16 | sync<<24, msg_off, magic}
+        const int nrows = (int)(sd.x >> 16);
+        if (sd.y >> 24) group_sync(c.G, c.bar);
+        const h2 msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && FIRST && ((sd.y >> 16) & 0xFF) >= 1) ? K.one : K.msg;
+        const int tasks = valid_pairs * nrows;
+        for (int t = c.gl; t < tasks; t += c.GT) {
+            const uint32_t p = ((uint32_t)t * sd.w) >> 16;
+            const uint32_t e = sd.z + ((uint32_t)t - p * nrows);
+            const uint32_t ub = c.state_s + p * c.pair_bytes;
+            uint32_t keep = 0u;
+            if (ET) keep = lds_u32(c.flags_s + 8u * p + 4u);
+            if (D > 0) rp_row<SEM, ALGO, (D > 0 ? D : 1), (D > 0 ? NR : 1), FIRST, ET, Q>(ub, ub + c.ms_off + 4u * e, c.idx_s + 2u * e, K, msg_c, keep);
+            else rp_row_generic<SEM, ALGO, FIRST, ET, Q>(ub, ub + c.ms_off + 4u * e, c.idx_s + 2u * e, (int)(sd.x & 0xFFFFu), (int)(sd.y & 0xFFFFu), K, msg_c, keep);
+        }
     }
 }
 
 template <int SEM, int ALGO, bool FIRST, bool ET, bool Q>
-__device__ __forceinline__ void rp_step(const RpStep& st, h2* U, h2* MS, const uint16_t* idx, int lane, const RowConsts& K, uint32_t keep)
+__device__ __forceinline__ void rp_dispatch(const RpCtx& c, const RpRun& r, int valid_pairs, const RowConsts& K)
 {
-    if (lane >= st.nrows) return;
-    const int a0 = st.msg_off + lane, stride = st.nrows;
-#define RP_CASE(DD) case DD: rp_row<SEM, ALGO, DD, FIRST, ET, Q>(U, MS, idx, a0, stride, K, keep); break;
-    switch (st.deg) {
-        RP_CASE(3) RP_CASE(4) RP_CASE(5) RP_CASE(6) RP_CASE(7) RP_CASE(8)
-    default: rp_row_generic<SEM, ALGO, FIRST, ET, Q>(U, MS, idx, a0, stride, st.deg, K, keep);
+#define RP_CASE(ID, DD, NN) case ID: rp_run<SEM, ALGO, DD, NN, FIRST, ET, Q>(c, r.first, r.count, valid_pairs, K); break;
+    switch (r.variant) {
+        RP_CASE(1, 6, 24) RP_CASE(2, 6, 32) RP_CASE(3, 7, 24) RP_CASE(4, 7, 32) RP_CASE(5, 8, 24) RP_CASE(6, 8, 32)
+    default: rp_run<SEM, ALGO, 0, 0, FIRST, ET, Q>(c, r.first, r.count, valid_pairs, K);
     }
 #undef RP_CASE
 }
 
 template <int SEM, int ALGO, bool FIRST, bool ET>
-__device__ __forceinline__ void rp_iteration(const RpStep* steps, int nsteps, h2* U, h2* MS, const uint16_t* idx, int lane, RowConsts& K, uint32_t keep)
+__device__ __forceinline__ void rp_iteration(const RpCtx& c, const RpRun* runs, int nruns, int valid_pairs, const RowConsts& K)
 {
-    for (int s = 0; s < nsteps; s++) {
-        const RpStep st = steps[s];
-        if (st.sync) __syncwarp();
-        K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && FIRST && st.cls >= 1) ? K.one : K.msg;
-        if (SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && st.cls >= 1) rp_step<SEM, ALGO, FIRST, ET, true>(st, U, MS, idx, lane, K, keep);
-        else rp_step<SEM, ALGO, FIRST, ET, false>(st, U, MS, idx, lane, K, keep);
+    for (int i = 0; i < nruns; i++) {
+        const RpRun r = runs[i];
+        // x86-SSE OMS clamps before the abs for rows of degree class >= 1 (ref: CDecoder_OMS_fixed_SSE.cpp:211 vs :293)
+        if (SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && r.quirk) rp_dispatch<SEM, ALGO, FIRST, ET, true>(c, r, valid_pairs, K);
+        else rp_dispatch<SEM, ALGO, FIRST, ET, false>(c, r, valid_pairs, K);
     }
-    __syncwarp();
+    group_sync(c.G, c.bar);
 }
 
-// per-frame syndrome criterion (see fp_syndrome): returns a word whose bit 15 / bit 31 says "some check of frame 0 / 1 failed"
-__device__ __forceinline__ uint32_t rp_syndrome(const RpStep* steps, int nsteps, const h2* U, const h2* MS, const uint16_t* idx, int lane,
-                                                const RowConsts& K, int lo)
+// per-frame syndrome criterion: parity of (x > 0) over every row, x = sat(v - m) with the UPDATED messages
+// (ref: code/ldpc_decoder_arm/CDecoder/OMS/CDecoder_OMS_fixed_x86.cpp:150-178).  ORs "some check failed" bits into flags[2p].
+__device__ __forceinline__ void rp_syndrome(const RpCtx& c, uint32_t* flags, int nsteps, int valid_pairs, const RowConsts& K, int lo)
 {
     const h2 lo_np = h2_const((float)(lo - 1) / 256.0f);
-    uint32_t bad = 0u;
     for (int s = 0; s < nsteps; s++) {
-        const RpStep st = steps[s];
-        if (lane < st.nrows) {
-            uint32_t p = (st.deg & 1) ? 0x80008000u : 0u;
-            for (int j = 0; j < st.deg; j++) {
-                const int a = st.msg_off + j * st.nrows + lane;
-                h2 xu = __hmin2(__hadd2_sat(U[idx[a]], __hneg2(MS[a])), K.top);
-                p ^= h2_bits(__hadd2(xu, lo_np));
+        const uint4 sd = lds_u128(c.steps_s + 32u * s);
+        const int nrows = (int)(sd.x >> 16), deg = (int)(sd.x & 0xFFFFu), stride = (int)(sd.y & 0xFFFFu);
+        const int tasks = valid_pairs * nrows;
+        for (int t = c.gl; t < tasks; t += c.GT) {
+            const uint32_t p = ((uint32_t)t * sd.w) >> 16;
+            const uint32_t e = sd.z + ((uint32_t)t - p * nrows);
+            const uint32_t ub = c.state_s + p * c.pair_bytes, msa = ub + c.ms_off + 4u * e, ixa = c.idx_s + 2u * e;
+            uint32_t par = (deg & 1) ? 0x80008000u : 0u;
+            for (int j = 0; j < deg; j++) {
+                const h2 u = bits_h2(lds_u32(ub + lds_u16(ixa + 2 * stride * j)));
+                const h2 xu = __hmin2(__hadd2_sat(u, __hneg2(bits_h2(lds_u32(msa + 4 * stride * j)))), K.top);
+                par ^= h2_bits(__hadd2(xu, lo_np));
             }
-            bad |= p;
+            par &= 0x80008000u;
+            if (par) atomicOr(&flags[2 * p], par);
         }
     }
-    bad &= 0x80008000u;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, d);
-    return bad;
 }
 
 // LLR int8 (two frames) -> biased binary16 posteriors of the pair
@@ -242,67 +305,114 @@ template <int SEM, int ALGO, bool ET>
 __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __grid_constant__ RpArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: steps | idx_t | per-warp { U[n_pad] , MS[m] }
+    // layout: steps | runs | idx | flags (2 words per pair slot) | pair states
     RpStep* steps = reinterpret_cast<RpStep*>(smem_raw);
-    uint16_t* idx = reinterpret_cast<uint16_t*>(steps + A.nsteps);
-    const size_t idx_bytes = (((size_t)A.m * 2 + 15) / 16) * 16;
-    h2* state = reinterpret_cast<h2*>(reinterpret_cast<unsigned char*>(idx) + idx_bytes);
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_pad = ((A.m + 3) / 4) * 4;
-    h2* U = state + (size_t)warp * (A.n_pad + m_pad);
-    h2* MS = U + A.n_pad;
+    RpRun* runs = reinterpret_cast<RpRun*>(steps + A.nsteps);
+    uint16_t* idx = reinterpret_cast<uint16_t*>(runs + A.nruns);
+    const size_t idx_bytes = (((size_t)A.m_elems * 2 + 15) / 16) * 16;
+    uint32_t* flags_all = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(idx) + idx_bytes);
+    const size_t flag_bytes = (((size_t)A.slots * 8 + 15) / 16) * 16;
+    unsigned char* state_all = reinterpret_cast<unsigned char*>(flags_all) + flag_bytes;
+    const int pair_bytes = A.pair_words * 4;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp / A.G, wig = warp - grp * A.G;
+    unsigned char* gstate = state_all + (size_t)grp * A.P * pair_bytes;
+    uint32_t* gflags = flags_all + 2 * grp * A.P;
+    const int gpairs = min(A.P, A.slots - grp * A.P);
+    RpCtx c;
+    c.steps_s = smem_u32(steps); c.idx_s = smem_u32(idx); c.flags_s = smem_u32(gflags); c.state_s = smem_u32(gstate);
+    c.pair_bytes = (uint32_t)pair_bytes; c.ms_off = 4u * A.n_pad;
+    c.gl = wig * 32 + lane; c.GT = A.G * 32; c.G = A.G; c.bar = 1 + grp;
 
     for (int i = threadIdx.x; i < A.nsteps * (int)(sizeof(RpStep) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(steps)[i] = reinterpret_cast<const uint32_t*>(A.steps)[i];
-    for (int i = threadIdx.x; i < A.m; i += blockDim.x) idx[i] = A.idx_t[i];
+    for (int i = threadIdx.x; i < A.nruns * 4; i += blockDim.x)
+        reinterpret_cast<int32_t*>(runs)[i] = reinterpret_cast<const int32_t*>(A.runs)[i];
+    for (int i = threadIdx.x; i < A.m_elems; i += blockDim.x) idx[i] = A.idx_t[i];
     __syncthreads();
 
     RowConsts K; make_consts<SEM>(K, A.prm);
     const int lo = (SEM == LDPC_SEM_GPU_FIXED) ? -128 : -A.prm.sat_var;
     const int hi = (SEM == LDPC_SEM_ARM_SCALAR) ? A.prm.sat_var : 127;
     const size_t pairs = (A.frames + 1) / 2;
-    for (size_t pair = (size_t)blockIdx.x * warps + warp; pair < pairs; pair += (size_t)gridDim.x * warps) {
-        const size_t f0 = 2 * pair;
-        rp_load_pair(A, f0, U, lane, lo, hi);
-        __syncwarp();
+    const size_t slot0 = (size_t)grp * A.P;
+    for (size_t base = (size_t)blockIdx.x * A.slots; base < pairs; base += (size_t)gridDim.x * A.slots) {
+        const size_t first = base + slot0;                 // global pair index of this group's pair 0
+        if (first >= pairs) break;                         // uniform over the group
+        const int valid = (int)min((size_t)gpairs, pairs - first);
+        {   // pull the NEXT set's LLRs into L2 while this set is decoded (the load below would otherwise expose HBM latency
+            // to the whole group once per set)
+            const size_t next = first + (size_t)gridDim.x * A.slots;
+            if (next < pairs) {
+                const size_t nvalid = min((size_t)gpairs, pairs - next);
+                const size_t bytes = min(nvalid * 2 * (size_t)A.n, (A.frames - 2 * next) * (size_t)A.n);
+                const char* src = reinterpret_cast<const char*>(A.llr) + 2 * next * (size_t)A.n;
+                for (size_t off = (size_t)c.gl * 128; off < bytes; off += (size_t)c.GT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
+            }
+        }
+        for (int p = wig; p < valid; p += A.G) {
+            rp_load_pair(A, 2 * (first + p), reinterpret_cast<h2*>(gstate + (size_t)p * pair_bytes), lane, lo, hi);
+            if (ET && lane == 0) { gflags[2 * p] = 0u; gflags[2 * p + 1] = 0u; }
+        }
+        group_sync(c.G, c.bar);
         int it = 0;
-        uint32_t done0 = 0u, done1 = 0u, keep = 0u;
+        uint32_t done_lo = 0u, done_hi = 0u;               // ET bookkeeping of pair gl lives in lane gl of the group
         if (A.iters > 0) {
-            rp_iteration<SEM, ALGO, true, ET>(steps, A.nsteps, U, MS, idx, lane, K, 0u);
+            rp_iteration<SEM, ALGO, true, ET>(c, runs, A.nruns, valid, K);
             it = 1;
             while (it < A.iters) {
                 if (ET) {
-                    const uint32_t bad = rp_syndrome(steps, A.nsteps, U, MS, idx, lane, K, lo);
-                    if (!(bad & 0x00008000u) && !done0) done0 = it;
-                    if (!(bad & 0x80000000u) && !done1) done1 = it;
-                    keep = (done0 ? 0x0000FFFFu : 0u) | (done1 ? 0xFFFF0000u : 0u);
-                    if (done0 && done1) break;
+                    rp_syndrome(c, gflags, A.nsteps, valid, K, lo);
+                    group_sync(c.G, c.bar);
+                    if (c.gl < valid) {
+                        const uint32_t bad = gflags[2 * c.gl];
+                        if (!(bad & 0x00008000u) && !done_lo) done_lo = it;
+                        if (!(bad & 0x80000000u) && !done_hi) done_hi = it;
+                        gflags[2 * c.gl] = (done_lo && done_hi) ? 0u : 1u;                                   // "still running"
+                        gflags[2 * c.gl + 1] = (done_lo ? 0x0000FFFFu : 0u) | (done_hi ? 0xFFFF0000u : 0u);  // freeze mask
+                    }
+                    group_sync(c.G, c.bar);
+                    uint32_t running = 0u;
+                    for (int p = 0; p < valid; p++) running |= gflags[2 * p];
+                    group_sync(c.G, c.bar);
+                    if (c.gl < valid) gflags[2 * c.gl] = 0u;       // cleared for the next syndrome pass (ordered by the barriers of the iteration)
+                    if (!running) break;
                 }
-                rp_iteration<SEM, ALGO, false, ET>(steps, A.nsteps, U, MS, idx, lane, K, keep);
+                rp_iteration<SEM, ALGO, false, ET>(c, runs, A.nruns, valid, K);
                 it++;
             }
         }
-        rp_store_pair(A, f0, U, lane, lo);
-        if (A.iters_done && lane == 0) {
-            A.iters_done[f0] = (uint8_t)((ET && done0) ? done0 : it);
-            if (f0 + 1 < A.frames) A.iters_done[f0 + 1] = (uint8_t)((ET && done1) ? done1 : it);
+        group_sync(c.G, c.bar);
+        if (A.iters_done && c.gl < valid) {
+            const size_t f0 = 2 * (first + c.gl);
+            A.iters_done[f0] = (uint8_t)((ET && done_lo) ? done_lo : it);
+            if (f0 + 1 < A.frames) A.iters_done[f0 + 1] = (uint8_t)((ET && done_hi) ? done_hi : it);
         }
-        if (A.dbg_post) {
-            for (int i = lane; i < A.n; i += 32) {
-                const uint32_t w = q_to_w(U[i], 0.0f);
-                A.dbg_post[f0 * (size_t)A.n + i] = (int8_t)((int)(w & 0xFFu) + lo);
-                if (f0 + 1 < A.frames) A.dbg_post[(f0 + 1) * (size_t)A.n + i] = (int8_t)((int)((w >> 16) & 0xFFu) + lo);
+        for (int p = wig; p < valid; p += A.G) {
+            const size_t f0 = 2 * (first + p);
+            const h2* U = reinterpret_cast<const h2*>(gstate + (size_t)p * pair_bytes);
+            const h2* MS = U + A.n_pad;
+            rp_store_pair(A, f0, U, lane, lo);
+            if (A.dbg_post) {
+                for (int i = lane; i < A.n; i += 32) {
+                    const uint32_t w = q_to_w(U[i], 0.0f);
+                    A.dbg_post[f0 * (size_t)A.n + i] = (int8_t)((int)(w & 0xFFu) + lo);
+                    if (f0 + 1 < A.frames) A.dbg_post[(f0 + 1) * (size_t)A.n + i] = (int8_t)((int)((w >> 16) & 0xFFu) + lo);
+                }
+            }
+            if (A.dbg_msgs) {
+                for (int i = lane; i < A.m_elems; i += 32) {
+                    const uint32_t e = A.edge_of[i];
+                    if (e == 0xFFFFFFFFu) continue;
+                    const uint32_t w = (A.iters > 0) ? q_to_w(MS[i], 128.0f) : 0x00800080u;
+                    A.dbg_msgs[f0 * (size_t)A.m + e] = (int8_t)((int)(w & 0xFFu) - 128);
+                    if (f0 + 1 < A.frames) A.dbg_msgs[(f0 + 1) * (size_t)A.m + e] = (int8_t)((int)((w >> 16) & 0xFFu) - 128);
+                }
             }
         }
-        if (A.dbg_msgs) {
-            for (int i = lane; i < A.m; i += 32) {
-                const uint32_t w = (A.iters > 0) ? q_to_w(MS[i], 128.0f) : 0x00800080u;
-                const size_t e = A.edge_of[i];
-                A.dbg_msgs[f0 * (size_t)A.m + e] = (int8_t)((int)(w & 0xFFu) - 128);
-                if (f0 + 1 < A.frames) A.dbg_msgs[(f0 + 1) * (size_t)A.m + e] = (int8_t)((int)((w >> 16) & 0xFFu) - 128);
-            }
-        }
-        __syncwarp();
+        group_sync(c.G, c.bar);
     }
 }
 

@@ -47,8 +47,8 @@ struct ldpc_b200_handle_s {
     int kernel = 0;                 // 1 = frame-parallel, 2 = row-parallel on-chip
     int levels = 0, sms = 0;
     // row-parallel plan
-    int rp_warps = 0, rp_npad = 0, rp_nsteps = 0; size_t rp_smem = 0;
-    RpStep* d_steps = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
+    int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0; size_t rp_smem = 0;
+    RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
     Slot slot[kSlots];
     bool debug = false;
@@ -109,20 +109,26 @@ int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& w
     return LDPC_OK;
 }
 
-// Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table.
-int build_rp_plan(ldpc_handle h, std::vector<RpStep>& steps, std::vector<uint16_t>& idx_t, std::vector<uint32_t>& edge_of)
+// Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table, (G, P) grouping.
+struct RpPlan {
+    std::vector<RpStep> steps; std::vector<RpRun> runs; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of;
+    int G = 1, P = 1, m_elems = 0, pair_pad = 0, slots = 0;
+};
+
+int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
 {
     const ldpc_code_t& c = h->code;
     std::vector<int32_t> level(c.n_checks);
     const int levels = ldpc_b200_level_schedule(&c, level.data());
     if (levels < 0) return levels;
     h->levels = levels;
-    std::vector<int> row_deg(c.n_checks), row_cls(c.n_checks); std::vector<uint32_t> row_e0(c.n_checks);
+    std::vector<int> row_cls(c.n_checks); std::vector<uint32_t> row_e0(c.n_checks);
     { int r = 0; uint32_t e = 0;
-      for (int k = 0; k < c.nb_deg; k++) for (int q = 0; q < c.rows[k]; q++, r++) { row_deg[r] = c.deg[k]; row_cls[r] = k; row_e0[r] = e; e += c.deg[k]; } }
+      for (int k = 0; k < c.nb_deg; k++) for (int q = 0; q < c.rows[k]; q++, r++) { row_cls[r] = k; row_e0[r] = e; e += c.deg[k]; } }
     std::vector<std::vector<int>> by_level(levels);
     for (int r = 0; r < c.n_checks; r++) by_level[level[r]].push_back(r);
-    idx_t.assign(c.m, 0); edge_of.assign(c.m, 0);
+    struct Tmp { RpStep st; std::vector<int> rows; };
+    std::vector<Tmp> tmp;
     int off = 0;
     for (int L = 0; L < levels; L++) {
         bool first = true;
@@ -135,19 +141,86 @@ int build_rp_plan(ldpc_handle h, std::vector<RpStep>& steps, std::vector<uint16_
             for (int q = 0; q < rounds; q++) {
                 const int b = q * per, e = std::min((int)rows.size(), b + per);
                 if (e <= b) continue;
-                RpStep st{}; st.deg = c.deg[k]; st.cls = k; st.nrows = e - b; st.msg_off = off; st.sync = first ? 1 : 0;
+                Tmp t; RpStep& st = t.st; memset(&st, 0, sizeof(st));
+                st.deg = (uint16_t)c.deg[k]; st.cls = (uint8_t)k; st.nrows = (uint16_t)(e - b); st.sync = first ? 1 : 0;
                 first = false;
-                for (int z = 0; z < st.nrows; z++)
-                    for (int j = 0; j < st.deg; j++) {
-                        const uint32_t ref_e = row_e0[rows[b + z]] + j;
-                        idx_t[off + j * st.nrows + z] = (uint16_t)c.pos[ref_e];
-                        edge_of[off + j * st.nrows + z] = ref_e;
-                    }
-                off += st.nrows * st.deg;
-                steps.push_back(st);
+                // specialised instantiations exist for degree 6..8 with an element stride of 24 or 32 (immediate addressing)
+                int stride = st.nrows;
+                if (st.deg >= 6 && st.deg <= 8 && st.nrows > 16) stride = st.nrows <= 24 ? 24 : 32;
+                st.stride = (uint16_t)stride;
+                st.variant = (uint32_t)rp_variant_id(st.deg, stride);
+                st.msg_off = (uint32_t)off;
+                st.magic = (65536u + st.nrows - 1) / st.nrows;
+                t.rows.assign(rows.begin() + b, rows.begin() + e);
+                off += stride * st.deg;
+                tmp.push_back(t);
             }
         }
     }
+    plan.m_elems = (off + 3) / 4 * 4;
+    plan.idx_t.assign(plan.m_elems, 0); plan.edge_of.assign(plan.m_elems, 0xFFFFFFFFu);
+    for (auto& t : tmp) {
+        const RpStep& st = t.st;
+        for (int z = 0; z < st.nrows; z++)
+            for (int j = 0; j < st.deg; j++) {
+                const uint32_t ref_e = row_e0[t.rows[z]] + j;
+                plan.idx_t[st.msg_off + j * st.stride + z] = (uint16_t)(4 * c.pos[ref_e]);
+                plan.edge_of[st.msg_off + j * st.stride + z] = ref_e;
+            }
+        plan.steps.push_back(st);
+    }
+    // runs: consecutive steps that share one kernel instantiation (degree, stride, x86 quirk class)
+    for (int i = 0; i < (int)plan.steps.size(); i++) {
+        const RpStep& st = plan.steps[i];
+        const int quirk = st.cls >= 1 ? 1 : 0;
+        if (!plan.runs.empty() && plan.runs.back().variant == (int)st.variant && plan.runs.back().quirk == quirk) plan.runs.back().count++;
+        else plan.runs.push_back(RpRun{ i, 1, (int)st.variant, quirk });
+    }
+    // grouping: G warps share P pairs so that the P*nrows tasks of a step fill whole warps.  Score = lane efficiency x
+    // occupancy (measured on 576x288, profiles/r01_sweep_groupings.jsonl: (3,4) with 18 warps 0.78 ms, (1,1) with 23 warps at
+    // 75 % lanes 0.86 ms, (1,4) with 100 % lanes but 6 warps 1.01 ms).
+    bool uniform = true;
+    for (auto& st : plan.steps) uniform = uniform && st.nrows == plan.steps[0].nrows;
+    const int nr0 = plan.steps[0].nrows;
+    const int base_words = (c.n + 3) / 4 * 4 + plan.m_elems;
+    auto pad_for = [&](int P) {
+        // a warp that straddles two pairs must not hit the same banks in both: pair pitch = nrows (mod 32 words) puts task t
+        // of a step in bank t % 32 whatever pair it belongs to
+        if (P > 1 && uniform && nr0 % 4 == 0) return ((nr0 % 32) - base_words % 32 + 32) % 32;
+        return 0;
+    };
+    auto slots_for = [&](int G, int P, int pad) {
+        const size_t pair_bytes = (size_t)(base_words + pad) * 4;
+        int slots = 0;
+        for (int s_try = 1; s_try <= 256; s_try++) {
+            const size_t fixed = plan.steps.size() * sizeof(RpStep) + plan.runs.size() * sizeof(RpRun) + (((size_t)plan.m_elems * 2 + 15) / 16) * 16 + (((size_t)s_try * 8 + 15) / 16) * 16;
+            const int groups = (s_try + P - 1) / P;
+            if (fixed + pair_bytes * s_try > smem_budget || groups * G > RP_MAX_THREADS / 32 || (G > 1 && groups > RP_MAX_GROUPS)) break;
+            slots = s_try;
+        }
+        return slots;
+    };
+    double best = -1.0;
+    for (int G = 1; G <= 4; G++)
+        for (int P = 1; P <= 8; P++) {
+            const int pad = pad_for(P), slots = slots_for(G, P, pad);
+            if (slots < 1) continue;
+            const int full = slots / P, rest = slots % P;
+            double useful = 0, issued = 0;
+            for (auto& st : plan.steps) {
+                const int lanes = 32 * G;
+                useful += (double)slots * st.nrows * st.deg;
+                issued += (double)full * ((P * st.nrows + lanes - 1) / lanes) * lanes * st.deg;
+                if (rest) issued += (double)((rest * st.nrows + lanes - 1) / lanes) * lanes * st.deg;
+            }
+            const int warps = (full + (rest ? 1 : 0)) * G;
+            const double score = useful / issued * std::min(1.0, warps / 16.0) - 0.002 * G * P;
+            if (score > best) { best = score; plan.G = G; plan.P = P; }
+        }
+    // experiment knob (not part of the reference's parameter set): reserved[0]/[1] force the grouping
+    if (h->prm.reserved[0] > 0 && h->prm.reserved[0] <= 4 && h->prm.reserved[1] > 0 && h->prm.reserved[1] <= 8) { plan.G = h->prm.reserved[0]; plan.P = h->prm.reserved[1]; }
+    plan.pair_pad = pad_for(plan.P);
+    plan.slots = slots_for(plan.G, plan.P, plan.pair_pad);
     return LDPC_OK;
 }
 
@@ -159,7 +232,7 @@ void destroy_impl(ldpc_handle h)
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG);
     }
-    cudaFree(h->d_steps); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos);
+    cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos);
     cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters);
     free(h->code.pos);
     delete h;
@@ -179,13 +252,15 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         a.llr = d_llr; a.hard = d_hard; a.iters_done = d_iters;
         a.dbg_post = want_debug ? h->d_dbg_post : nullptr; a.dbg_msgs = want_debug ? h->d_dbg_msgs : nullptr;
         a.idx_t = h->d_idx_t; a.edge_of = h->d_edge_of; a.steps = h->d_steps;
-        a.frames = frames; a.n = c.n; a.m = c.m; a.nsteps = h->rp_nsteps; a.n_pad = h->rp_npad; a.iters = iters;
+        a.runs = h->d_runs; a.nruns = h->rp_nruns; a.pair_words = h->rp_pair_words;
+        a.frames = frames; a.n = c.n; a.m = c.m; a.nsteps = h->rp_nsteps; a.n_pad = h->rp_npad; a.m_elems = h->rp_melems;
+        a.G = h->rp_G; a.P = h->rp_P; a.groups = h->rp_groups; a.slots = h->rp_slots; a.iters = iters;
         a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.prm = h->prm;
         const size_t pairs = (frames + 1) / 2;
-        const int blocks = (int)std::min<size_t>((size_t)h->sms, (pairs + h->rp_warps - 1) / h->rp_warps);
+        const int blocks = (int)std::min<size_t>((size_t)h->sms, (pairs + h->rp_slots - 1) / h->rp_slots);
         rp_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_rp_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_rp_uniform
                         : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_rp_arm : launch_rp_gpu;
-        CU_TRY(h, (cudaError_t)fn(h->prm.algo, et, a, blocks, h->rp_warps * 32, h->rp_smem, st));
+        CU_TRY(h, (cudaError_t)fn(h->prm.algo, et, a, blocks, h->rp_groups * h->rp_G * 32, h->rp_smem, st));
         h->launches += 1;
         return LDPC_OK;
     }
@@ -290,33 +365,38 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     CREATE_TRY(cudaMalloc((void**)&h->d_counters, 2 * sizeof(unsigned long long)));
 
     // kernel selection: the on-chip row-parallel kernel needs the whole state of >= 8 frame pairs per SM in shared memory
-    std::vector<RpStep> steps; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of;
     h->kernel = 1;
-    if (code->n <= 65535 && params->kernel != 1) {
-        if ((rc = build_rp_plan(h, steps, idx_t, edge_of))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
+    if (code->n <= 16383 && params->kernel != 1) {
+        RpPlan plan;
+        if ((rc = build_rp_plan(h, plan, (size_t)prop.sharedMemPerBlockOptin))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
         h->rp_npad = (code->n + 3) / 4 * 4;
-        const int m_pad = (code->m + 3) / 4 * 4;
-        const size_t fixed = steps.size() * sizeof(RpStep) + (((size_t)code->m * 2 + 15) / 16) * 16;
-        const size_t per_warp = (size_t)(h->rp_npad + m_pad) * 4;
-        const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
-        int warps = budget > fixed ? (int)((budget - fixed) / per_warp) : 0;
-        warps = std::min(warps, RP_MAX_THREADS / 32);
-        const int min_warps = params->kernel == 2 ? 1 : 8;
-        if (warps >= min_warps) {
-            h->kernel = 2; h->rp_warps = warps; h->rp_nsteps = (int)steps.size(); h->rp_smem = fixed + per_warp * warps;
-            CREATE_TRY(cudaMalloc((void**)&h->d_steps, steps.size() * sizeof(RpStep)));
-            CREATE_TRY(cudaMemcpy(h->d_steps, steps.data(), steps.size() * sizeof(RpStep), cudaMemcpyHostToDevice));
-            CREATE_TRY(cudaMalloc((void**)&h->d_idx_t, idx_t.size() * sizeof(uint16_t)));
-            CREATE_TRY(cudaMemcpy(h->d_idx_t, idx_t.data(), idx_t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-            CREATE_TRY(cudaMalloc((void**)&h->d_edge_of, edge_of.size() * sizeof(uint32_t)));
-            CREATE_TRY(cudaMemcpy(h->d_edge_of, edge_of.data(), edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        h->rp_melems = plan.m_elems;
+        h->rp_pair_words = h->rp_npad + plan.m_elems + plan.pair_pad;
+        const size_t pair_bytes = (size_t)h->rp_pair_words * 4;
+        auto fixed_bytes = [&](int slots_) { return plan.steps.size() * sizeof(RpStep) + plan.runs.size() * sizeof(RpRun) + (((size_t)plan.m_elems * 2 + 15) / 16) * 16 + (((size_t)slots_ * 8 + 15) / 16) * 16; };
+        const int slots = plan.slots;
+        const int min_slots = params->kernel == 2 ? 1 : 8;
+        if (slots >= min_slots) {
+            h->kernel = 2; h->rp_G = plan.G; h->rp_P = plan.P; h->rp_slots = slots; h->rp_groups = (slots + plan.P - 1) / plan.P;
+            h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size();
+            h->rp_smem = fixed_bytes(slots) + pair_bytes * slots;
+            CREATE_TRY(cudaMalloc((void**)&h->d_runs, plan.runs.size() * sizeof(RpRun)));
+            CREATE_TRY(cudaMemcpy(h->d_runs, plan.runs.data(), plan.runs.size() * sizeof(RpRun), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_steps, plan.steps.size() * sizeof(RpStep)));
+            CREATE_TRY(cudaMemcpy(h->d_steps, plan.steps.data(), plan.steps.size() * sizeof(RpStep), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_idx_t, plan.idx_t.size() * sizeof(uint16_t)));
+            CREATE_TRY(cudaMemcpy(h->d_idx_t, plan.idx_t.data(), plan.idx_t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_edge_of, plan.edge_of.size() * sizeof(uint32_t)));
+            CREATE_TRY(cudaMemcpy(h->d_edge_of, plan.edge_of.data(), plan.edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the row-parallel kernel"); }
-    } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 65535"); }
+    } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 16383"); }
     if (h->kernel == 1 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
 #undef CREATE_TRY
     // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
-    size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_warps * 2 : (size_t)h->sms * 512 * 4;
-    h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, std::max<size_t>(h->max_frames / 4, 2 * wave)), 1);
+    // a whole number of waves of the chosen kernel, about a fifth of the declared capacity
+    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : (size_t)h->sms * 512 * 4;
+    const size_t k = std::max<size_t>(1, (h->max_frames / 5 + wave / 2) / wave);
+    h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
     *out = h;
     return LDPC_OK;
 }
@@ -330,7 +410,7 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     case LDPC_INFO_KERNEL: *value = h->kernel; break;
     case LDPC_INFO_LEVELS: *value = h->levels; break;
     case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : 16384; break;
-    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_warps * 2 : FP_BLOCK * 4; break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : FP_BLOCK * 4; break;
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;

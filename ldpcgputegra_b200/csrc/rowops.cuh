@@ -117,13 +117,21 @@ struct RowOut {
     uint32_t sgn;  // bit 15 of each half = row parity ^ degree parity ; other bits = 1.0 (0x3C00)
 };
 
+// (a & b) ^ c in one LOP3; written in PTX so the compiler cannot re-associate the parity xors into every edge
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 template <int SEM, int ALGO>
-__device__ __forceinline__ void row_finish(const RowState& s, int deg, const RowConsts& K, RowOut& o)
+__device__ __forceinline__ void row_finish(const RowState& s, int deg, const RowConsts& K, h2 msg_c, RowOut& o)
 {
     h2 c1, c2;
     if (ALGO == LDPC_ALGO_OMS) {
-        c1 = __hmin2(__hadd2_sat(s.min2, K.off), K.msg_c);     // min(max(min-offset,0), sat_msg) (ref: CDecoder_OMS_fixed_SSE.cpp:229-230)
-        c2 = __hmin2(__hadd2_sat(s.min1, K.off), K.msg_c);
+        c1 = __hmin2(__hadd2_sat(s.min2, K.off), msg_c);       // min(max(min-offset,0), sat_msg) (ref: CDecoder_OMS_fixed_SSE.cpp:229-230)
+        c2 = __hmin2(__hadd2_sat(s.min1, K.off), msg_c);
     } else if (ALGO == LDPC_ALGO_MS) {
         c1 = __hmin2(s.min2, K.msg); c2 = __hmin2(s.min1, K.msg);   // (ref: CUDA_MS_SIMD.cu:173-174)
     } else {
@@ -132,7 +140,56 @@ __device__ __forceinline__ void row_finish(const RowState& s, int deg, const Row
     o.c1 = c1;
     o.dc = __hsub2(c2, c1);
     o.nmin1 = __hneg2(__hmul2(s.min1, K.k256));
-    o.sgn = ((s.par ^ ((deg & 1) ? 0x80008000u : 0u)) & 0x80008000u) | 0x3C003C00u;
+    o.sgn = and_xor(s.par, 0x80008000u, ((deg & 1) ? 0x80008000u : 0u) | 0x3C003C00u);
+}
+
+// ---- register-resident row update used by the on-chip kernel: all D contributions of a row are in registers -------------
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// merge two new magnitudes into the running (min1, min2): 5 min/max ops per 2 edges instead of 6
+__device__ __forceinline__ void track2(RowState& s, h2 a, h2 b)
+{
+    const h2 p = __hmin2(a, b), q = __hmax2(a, b);
+    const h2 n1 = __hmin2(s.min1, p);
+    s.min2 = __hmin2(__hmin2(__hmax2(s.min1, p), s.min2), q);
+    s.min1 = n1;
+}
+__device__ __forceinline__ void track1(RowState& s, h2 a)
+{
+    const h2 old = s.min1;
+    s.min1 = __hmin2(s.min1, a);
+    s.min2 = __hmin2(s.min2, __hmax2(a, old));
+}
+
+// pass 1 over a whole row: xu[] in, a[] (magnitudes) and f[] (words whose sign bits are the parity flags) out
+template <int SEM, int ALGO, bool Q, int D>
+__device__ __forceinline__ void row_pass1(const h2 (&xu)[D], h2 (&a)[D], uint32_t (&f)[D], RowState& s, const RowConsts& K)
+{
+    row_begin(s, K);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const h2 t = signed_contrib(xu[j], K);
+        a[j] = magnitude<SEM, ALGO, Q>(t, K);
+        f[j] = (SEM == LDPC_SEM_GPU_FIXED || SEM == LDPC_SEM_ARM_SCALAR) ? h2_bits(__hadd2(xu[j], K.lo_flag)) : h2_bits(t);
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < D; j += 2) { track2(s, a[j], a[j + 1]); s.par = xor3(s.par, f[j], f[j + 1]); }
+    if (D & 1) { track1(s, a[D - 1]); s.par ^= f[D - 1]; }
+}
+
+// pass 2, one edge, flag word from pass 1
+__device__ __forceinline__ void pass2_edge_f(h2 xu, h2 a, uint32_t f, const RowOut& o, const RowConsts& K, h2& msg, h2& unew)
+{
+    const h2 d = __hfma2_sat(a, K.k256, o.nmin1);
+    const h2 mag = __hfma2(d, o.dc, o.c1);
+    const h2 sigma = bits_h2(and_xor(f, 0x80008000u, o.sgn));
+    msg = __hmul2(sigma, mag);
+    unew = __hmin2(__hfma2_sat(sigma, mag, xu), K.top);
 }
 
 // pass 2, one edge: returns the new message (signed, /256) and the new biased posterior
@@ -142,7 +199,7 @@ __device__ __forceinline__ void pass2_edge(h2 xu, h2 a, const RowOut& o, const R
     h2 flag = (SEM == LDPC_SEM_GPU_FIXED || SEM == LDPC_SEM_ARM_SCALAR) ? __hadd2(xu, K.lo_flag) : signed_contrib(xu, K);
     h2 d = __hfma2_sat(a, K.k256, o.nmin1);                    // 0 where a == min1, 1 elsewhere
     h2 mag = __hfma2(d, o.dc, o.c1);                           // c1 or c2
-    h2 sigma = bits_h2((h2_bits(flag) & 0x80008000u) ^ o.sgn); // +-1.0
+    h2 sigma = bits_h2(and_xor(h2_bits(flag), 0x80008000u, o.sgn)); // +-1.0
     msg = __hmul2(sigma, mag);
     unew = __hmin2(__hfma2_sat(sigma, mag, xu), K.top);        // saturating add at both rails
 }
