@@ -21,7 +21,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "libldpc_b200.so"
+_LIB_PATH = Path(os.environ.get("LDPC_B200_LIB", _PKG / "libldpc_b200.so"))   # override = A/B experiments only
 CODES_DIR = _PKG / "codes"
 
 MAX_DEG_CLASSES = 8
@@ -187,6 +187,9 @@ def default_params(**kw) -> ParamsT:
             v = ALGO[v]
         if k == "semantics" and isinstance(v, str):
             v = SEM[v]
+        if k == "chunk_waves":    # waves per pipeline chunk of decode() (experiment knob)
+            p.reserved[2] = v
+            continue
         if k == "group":          # (G warps, P pairs) experiment knob of the on-chip kernel
             p.reserved[0], p.reserved[1] = v
             continue

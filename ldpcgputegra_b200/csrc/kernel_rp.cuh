@@ -335,17 +335,19 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
     RowConsts K; make_consts<SEM>(K, A.prm);
     const int lo = (SEM == LDPC_SEM_GPU_FIXED) ? -128 : -A.prm.sat_var;
     const int hi = (SEM == LDPC_SEM_ARM_SCALAR) ? A.prm.sat_var : 127;
-    const size_t pairs = (A.frames + 1) / 2;
-    const size_t slot0 = (size_t)grp * A.P;
-    for (size_t base = (size_t)blockIdx.x * A.slots; base < pairs; base += (size_t)gridDim.x * A.slots) {
-        const size_t first = base + slot0;                 // global pair index of this group's pair 0
+    // 32-bit pair arithmetic in the loop (a launch never carries 2^31 pairs; the host chunks): 64-bit bounds made the compiler
+    // re-derive min(gpairs, pairs - first) with wide ops in every step
+    const uint32_t pairs = (uint32_t)((A.frames + 1) / 2);
+    const uint32_t slot0 = (uint32_t)(grp * A.P);
+    for (uint32_t base = blockIdx.x * (uint32_t)A.slots; base < pairs; base += gridDim.x * (uint32_t)A.slots) {
+        const uint32_t first = base + slot0;               // global pair index of this group's pair 0
         if (first >= pairs) break;                         // uniform over the group
-        const int valid = (int)min((size_t)gpairs, pairs - first);
+        const int valid = (int)min((uint32_t)gpairs, pairs - first);
         {   // pull the NEXT set's LLRs into L2 while this set is decoded (the load below would otherwise expose HBM latency
             // to the whole group once per set)
-            const size_t next = first + (size_t)gridDim.x * A.slots;
+            const size_t next = (size_t)first + (size_t)gridDim.x * A.slots;
             if (next < pairs) {
-                const size_t nvalid = min((size_t)gpairs, pairs - next);
+                const size_t nvalid = min((size_t)gpairs, (size_t)pairs - next);
                 const size_t bytes = min(nvalid * 2 * (size_t)A.n, (A.frames - 2 * next) * (size_t)A.n);
                 const char* src = reinterpret_cast<const char*>(A.llr) + 2 * next * (size_t)A.n;
                 for (size_t off = (size_t)c.gl * 128; off < bytes; off += (size_t)c.GT * 128)
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
             }
         }
         for (int p = wig; p < valid; p += A.G) {
-            rp_load_pair(A, 2 * (first + p), reinterpret_cast<h2*>(gstate + (size_t)p * pair_bytes), lane, lo, hi);
+            rp_load_pair(A, 2 * ((size_t)first + p), reinterpret_cast<h2*>(gstate + (size_t)p * pair_bytes), lane, lo, hi);
             if (ET && lane == 0) { gflags[2 * p] = 0u; gflags[2 * p + 1] = 0u; }
         }
         group_sync(c.G, c.bar);
@@ -386,12 +388,12 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
         }
         group_sync(c.G, c.bar);
         if (A.iters_done && c.gl < valid) {
-            const size_t f0 = 2 * (first + c.gl);
+            const size_t f0 = 2 * ((size_t)first + c.gl);
             A.iters_done[f0] = (uint8_t)((ET && done_lo) ? done_lo : it);
             if (f0 + 1 < A.frames) A.iters_done[f0 + 1] = (uint8_t)((ET && done_hi) ? done_hi : it);
         }
         for (int p = wig; p < valid; p += A.G) {
-            const size_t f0 = 2 * (first + p);
+            const size_t f0 = 2 * ((size_t)first + p);
             const h2* U = reinterpret_cast<const h2*>(gstate + (size_t)p * pair_bytes);
             const h2* MS = U + A.n_pad;
             rp_store_pair(A, f0, U, lane, lo);

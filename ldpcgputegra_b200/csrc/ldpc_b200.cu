@@ -393,9 +393,12 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     if (h->kernel == 1 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
 #undef CREATE_TRY
     // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
-    // a whole number of waves of the chosen kernel, about a fifth of the declared capacity
+    // pipeline granularity of decode(): whole waves of the chosen kernel.  H2D, kernel and D2H take about the same time per
+    // frame for 576x288 over PCIe Gen5, so the fill/drain of the 3-stage pipeline costs 2 chunks: many small chunks win
+    // (measured: 5 chunks 1.17 ms, 10 chunks of one wave each — see profiles/r01_e2e_chunks.txt).  reserved[2] overrides (waves per chunk).
     const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : (size_t)h->sms * 512 * 4;
-    const size_t k = std::max<size_t>(1, (h->max_frames / 5 + wave / 2) / wave);
+    size_t k = h->kernel == 2 ? 1 : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
+    if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
     *out = h;
     return LDPC_OK;
