@@ -59,6 +59,15 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
+    def sample_once(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+
     def run(self):
         if not self.nv:
             return
@@ -74,7 +83,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag = True
@@ -101,7 +110,7 @@ def cpu_reference_run(llr: np.ndarray, min_seconds: float, threads: int):
     if L is not None:
         kind = "reference"
         L.ref_x86_decode_mt(ALGO["OMS"], 1, llr.ctypes.data, hard.ctypes.data, min(F, 16 * threads * 4), ITERS, threads)   # warm-up
-        while spent < min_seconds:
+        while reps == 0 or spent < min_seconds:
             t = L.ref_x86_decode_mt(ALGO["OMS"], 1, llr.ctypes.data, hard.ctypes.data, F, ITERS, threads)
             if t < 0:
                 raise RuntimeError("ref_x86_decode_mt failed")
@@ -110,11 +119,11 @@ def cpu_reference_run(llr: np.ndarray, min_seconds: float, threads: int):
         kind = "port"
         code = Code.load(CODE)
         prm = default_params()
-        while spent < min_seconds:
+        while reps == 0 or spent < min_seconds:
             t0 = time.perf_counter()
             hard = oracle_decode_mt(code, prm, llr, ITERS, threads)
             spent += time.perf_counter() - t0; reps += 1
-    return F * reps / spent, kind, f"{F} frames x {reps} passes ({spent:.1f} s wall on {threads} threads)", hard
+    return F * reps / max(spent, 1e-9), kind, f"{F} frames x {reps} passes ({spent:.1f} s wall on {threads} threads)", hard
 
 
 def main():
@@ -217,6 +226,7 @@ def main():
     for i in range(steps):
         dec.decode_device(d_llr[i % NBUF].data_ptr(), d_hard.data_ptr(), F, ITERS, stream=stream)
     e1.record()
+    sampler.sample_once()                        # the launches above are asynchronous: the GPU is inside the timed region here
     torch.cuda.synchronize()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = dec.info(pkg.INFO_LAUNCHES) - l0

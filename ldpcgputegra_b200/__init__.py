@@ -27,6 +27,9 @@ CODES_DIR = _PKG / "codes"
 MAX_DEG_CLASSES = 8
 ALGO = {"MS": 0, "OMS": 1, "NMS": 2, "2NMS": 3}
 SEM = {"X86_SSE": 0, "UNIFORM": 1, "ARM_SCALAR": 2, "GPU_FIXED": 3}
+SCHED = {"LAYERED": 0, "FLOODING": 1}
+DTYPE = {"I8": 0, "I16": 1, "F32": 2}
+NP_DTYPE = {0: np.int8, 1: np.int16, 2: np.float32}
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_IO, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 INFO_KERNEL, INFO_LEVELS, INFO_SMEM_BYTES, INFO_FRAMES_PER_CTA, INFO_LAUNCHES, INFO_STREAM_SLOTS, INFO_DEVICE = range(7)
 
@@ -187,6 +190,10 @@ def default_params(**kw) -> ParamsT:
             v = ALGO[v]
         if k == "semantics" and isinstance(v, str):
             v = SEM[v]
+        if k == "schedule" and isinstance(v, str):
+            v = SCHED[v]
+        if k == "dtype" and isinstance(v, str):
+            v = DTYPE[v]
         if k == "chunk_waves":    # waves per pipeline chunk of decode() (experiment knob)
             p.reserved[2] = v
             continue
@@ -227,6 +234,7 @@ class CGPUDecoder:
         self.code = code
         self.params = params if params is not None else default_params(**kw)
         self._h = C.c_void_p()
+        self.np_dtype = NP_DTYPE.get(self.params.dtype, np.int8)     # element type of LLRs / posteriors / messages at the boundary
         c = code.c_struct()
         _check(lib().ldpc_b200_create(C.byref(self._h), C.byref(c), C.byref(self.params), device, nb_frames))
 
@@ -260,8 +268,9 @@ class CGPUDecoder:
         return q
 
     def decode(self, llr: np.ndarray, iterations: int, out: np.ndarray | None = None, want_iters: bool = False):
-        """llr: int8 [frames, n] (host).  Returns hard decisions [frames, n] bytes in {0,1} (or packed), optionally iteration counts."""
-        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        """llr: [frames, n] (host) of the handle's dtype (int8 / int16 / float32).  Returns hard decisions [frames, n] bytes in
+        {0,1} (or packed), optionally iteration counts."""
+        llr = np.ascontiguousarray(llr, dtype=self.np_dtype)
         frames = llr.shape[0] if llr.ndim == 2 else llr.size // self.code.n
         if out is None:
             out = np.empty((frames, self.hard_row_bytes), dtype=np.uint8)
@@ -285,13 +294,13 @@ class CGPUDecoder:
         _check(lib().ldpc_b200_set_debug(self._h, int(on)), self._h)
 
     def debug_state(self, frames: int):
-        post = np.empty((frames, self.code.n), dtype=np.int8)
-        msgs = np.empty((frames, self.code.m), dtype=np.int8)
+        post = np.empty((frames, self.code.n), dtype=self.np_dtype)
+        msgs = np.empty((frames, self.code.m), dtype=self.np_dtype)
         _check(lib().ldpc_b200_debug_state(self._h, post.ctypes.data, msgs.ctypes.data, frames), self._h)
         return post, msgs
 
     def awgn(self, frames: int, sigma: float, seed: int, first_frame: int = 0) -> np.ndarray:
-        q = np.empty((frames, self.code.n), dtype=np.int8)
+        q = np.empty((frames, self.code.n), dtype=self.np_dtype)
         _check(lib().ldpc_b200_awgn(self._h, q.ctypes.data, frames, sigma, seed, first_frame), self._h)
         return q
 

@@ -42,8 +42,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     }
 }
 
+// channel value -> the decoder's input type: quantised int8 / int16, or the raw float y (norm_channel = false: no 2/sigma^2
+// scaling, ref: code/x86/main_p.cpp:124)
+template <class S> __device__ __forceinline__ S awgn_out(float y, float scale, int sat) { return (S)quantize_one(__fmul_rn(scale, y), sat); }
+template <> __device__ __forceinline__ float awgn_out<float>(float y, float, int) { return y; }
+
 // one thread = 4 consecutive positions of one frame
-__global__ void awgn_kernel(int8_t* __restrict__ q, size_t frames, int n, float sigma, uint64_t seed, uint64_t first_frame, float scale, int sat)
+template <class S>
+__global__ void awgn_kernel(S* __restrict__ q, size_t frames, int n, float sigma, uint64_t seed, uint64_t first_frame, float scale, int sat)
 {
     const int quads = (n + 3) / 4;
     const size_t total = frames * (size_t)quads;
@@ -66,7 +72,7 @@ __global__ void awgn_kernel(int8_t* __restrict__ q, size_t frames, int n, float 
         for (int b = 0; b < 4; b++) {
             if (p + b < n) {
                 const float y = -1.0f + sigma * g[b];
-                q[f * (size_t)n + p + b] = (int8_t)quantize_one(__fmul_rn(scale, y), sat);
+                q[f * (size_t)n + p + b] = awgn_out<S>(y, scale, sat);
             }
         }
     }

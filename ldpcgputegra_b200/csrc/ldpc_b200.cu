@@ -19,6 +19,7 @@
 #include "boundary.cuh"
 #include "channel.cuh"
 #include "launch.cuh"
+#include "kernel_gp.cuh"
 
 using namespace ldpcb200;
 
@@ -34,6 +35,7 @@ struct Slot {
     uint8_t* d_iters = nullptr;  size_t iters_bytes = 0;
     uint32_t* d_V = nullptr;     size_t v_bytes = 0;       // frame-parallel kernel state
     uint32_t* d_MSG = nullptr;   size_t msg_bytes = 0;
+    uint8_t* d_LLR0 = nullptr;   size_t llr0_bytes = 0;    // generic engine, flooding: interleaved channel values
     int T = 0;                                              // words per variable the V/MSG buffers were laid out for
 };
 
@@ -44,7 +46,10 @@ struct ldpc_b200_handle_s {
     ldpc_code_t code{};
     ldpc_params_t prm{};
     size_t max_frames = 0, chunk_frames = 0;
-    int kernel = 0;                 // 1 = frame-parallel, 2 = row-parallel on-chip
+    int kernel = 0;                 // 1 = frame-parallel, 2 = row-parallel on-chip, 3 = generic engine (fp32 arithmetic)
+    int elem = 1;                   // bytes per LLR / posterior / message element at the boundary (1, 2 or 4)
+    GpMode gp_mode{};
+    int32_t* d_cptr = nullptr; int32_t* d_cedge = nullptr;
     int levels = 0, sms = 0;
     // row-parallel plan
     int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0; size_t rp_smem = 0;
@@ -52,7 +57,7 @@ struct ldpc_b200_handle_s {
     uint32_t* d_pos = nullptr;
     Slot slot[kSlots];
     bool debug = false;
-    int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_frames_cap = 0, dbg_frames = 0; int dbg_iters = 0;
+    int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_post_bytes = 0, dbg_msgs_bytes = 0, dbg_frames = 0; int dbg_iters = 0;
     unsigned long long* d_counters = nullptr;
     int64_t launches = 0;
     std::string err;
@@ -85,28 +90,66 @@ int ensure(ldpc_handle h, T** p, size_t* have, size_t need)
 
 int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& why)
 {
-    if (p->dtype != LDPC_DTYPE_I8) { why = "only LDPC_DTYPE_I8 is implemented on the GPU in this build"; return LDPC_ERR_UNSUPPORTED; }
-    if (p->schedule != LDPC_SCHED_LAYERED) { why = "only the layered schedule is implemented for fixed point (the reference has no flooding decoder)"; return LDPC_ERR_UNSUPPORTED; }
+    if (p->dtype != LDPC_DTYPE_I8 && p->dtype != LDPC_DTYPE_I16 && p->dtype != LDPC_DTYPE_F32) { why = "unknown dtype"; return LDPC_ERR_INVALID; }
+    if (p->schedule != LDPC_SCHED_LAYERED && p->schedule != LDPC_SCHED_FLOODING) { why = "unknown schedule"; return LDPC_ERR_INVALID; }
+    if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
+    if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
+    if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
+    if (p->kernel < 0 || p->kernel > 3) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
+    const bool generic = p->dtype != LDPC_DTYPE_I8 || p->schedule != LDPC_SCHED_LAYERED;
+    if (generic && (p->kernel == 1 || p->kernel == 2)) { why = "kernels 1 and 2 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
+    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3)) { why = "generic engine: row degree > 64"; return LDPC_ERR_UNSUPPORTED; }
+    if (p->dtype == LDPC_DTYPE_F32) {
+        if (p->algo == LDPC_ALGO_OMS && (p->offset < 0 || p->llr_scale <= 0)) { why = "float OMS: offset >= 0 and llr_scale > 0 (offset is offset/llr_scale in channel units)"; return LDPC_ERR_INVALID; }
+        if ((p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS) && !(p->factor1 > 0.0f && p->factor2 > 0.0f)) { why = "float NMS: factors must be positive"; return LDPC_ERR_INVALID; }
+        return LDPC_OK;
+    }
+    const bool wide = p->dtype == LDPC_DTYPE_I16;
+    const int rail = wide ? 32767 : 127;
     switch (p->semantics) {
-    case LDPC_SEM_X86_SSE: case LDPC_SEM_UNIFORM:
+    case LDPC_SEM_X86_SSE:
+        if (wide) { why = "int16: UNIFORM or ARM_SCALAR semantics (the SSE decoder is int8 only, CDecoder_OMS_fixed_SSE.cpp:114-120)"; return LDPC_ERR_UNSUPPORTED; }
+        /* fall through */
+    case LDPC_SEM_UNIFORM:
         if (p->algo != LDPC_ALGO_OMS && p->algo != LDPC_ALGO_NMS) { why = "x86 semantics: OMS or NMS only"; return LDPC_ERR_UNSUPPORTED; }
-        if (p->sat_var != 127) { why = "x86 semantics: sat_var must be 127 (the reference exits otherwise, CDecoder_OMS_fixed_SSE.cpp:114-120)"; return LDPC_ERR_INVALID; }
+        if (!wide && p->sat_var != 127) { why = "x86 semantics: sat_var must be 127 (the reference exits otherwise, CDecoder_OMS_fixed_SSE.cpp:114-120)"; return LDPC_ERR_INVALID; }
+        if (wide && (p->sat_var < 1 || p->sat_var > rail)) { why = "int16 path: 1 <= sat_var <= 32767"; return LDPC_ERR_INVALID; }
         break;
     case LDPC_SEM_ARM_SCALAR:
         if (p->algo != LDPC_ALGO_OMS) { why = "ARM scalar semantics: OMS only"; return LDPC_ERR_UNSUPPORTED; }
-        if (p->sat_var < 1 || p->sat_var > 127) { why = "int8 path: 1 <= sat_var <= 127"; return LDPC_ERR_INVALID; }
+        if (p->sat_var < 1 || p->sat_var > rail) { why = wide ? "int16 path: 1 <= sat_var <= 32767" : "int8 path: 1 <= sat_var <= 127"; return LDPC_ERR_INVALID; }
         break;
-    case LDPC_SEM_GPU_FIXED: break;
+    case LDPC_SEM_GPU_FIXED:
+        if (wide) { why = "int16: UNIFORM or ARM_SCALAR semantics (the gpu_fixed kernels are int8x4 only)"; return LDPC_ERR_UNSUPPORTED; }
+        break;
     default: why = "unknown semantics"; return LDPC_ERR_INVALID;
     }
-    if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
-    if (p->sat_msg < 1 || p->sat_msg > 127 || p->offset < 0 || p->offset > 127) { why = "sat_msg/offset out of range"; return LDPC_ERR_INVALID; }
+    if (p->sat_msg < 1 || p->sat_msg > rail || p->offset < 0 || p->offset > rail) { why = "sat_msg/offset out of range"; return LDPC_ERR_INVALID; }
     if (p->factor_q5 < 0 || p->factor_q5 > 255) { why = "factor_q5 must be in [0,255]"; return LDPC_ERR_INVALID; }
     if (p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS)
         for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] < 2) { why = "NMS needs row degree >= 2"; return LDPC_ERR_UNSUPPORTED; }
-    if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
-    if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
     return LDPC_OK;
+}
+
+GpMode make_gp_mode(const ldpc_params_t& p)
+{
+    GpMode md{};
+    md.is_float = p.dtype == LDPC_DTYPE_F32; md.wide = p.dtype == LDPC_DTYPE_I16;
+    md.sem = p.semantics; md.algo = p.algo;
+    const bool gpu = !md.is_float && p.semantics == LDPC_SEM_GPU_FIXED, arm = !md.is_float && p.semantics == LDPC_SEM_ARM_SCALAR;
+    md.lo = gpu ? -128.0f : -(float)p.sat_var;
+    md.hi = (arm || md.wide) ? (float)p.sat_var : 127.0f;
+    md.sat_msg = gpu ? 31.0f : (float)p.sat_msg;
+    md.off = md.is_float ? (float)p.offset / (float)p.llr_scale : (gpu ? 1.0f : (float)p.offset);
+    if (md.is_float) {
+        md.f1 = p.algo == LDPC_ALGO_MS ? 1.0f : p.factor1;
+        md.f2 = p.algo == LDPC_ALGO_MS ? 1.0f : (p.algo == LDPC_ALGO_2NMS ? p.factor2 : p.factor1);
+    } else { md.f1 = 0.75f; md.f2 = p.algo == LDPC_ALGO_2NMS ? 0.875f : 0.75f; }   // GPU_FIXED literals (CUDA_NMS_SIMD.cu:76-83, CUDA_2NMS_SIMD.cu:76-83)
+    md.factor = (float)p.factor_q5; md.pack_sat = md.wide ? 32767.0f : 127.0f;
+    md.min_init = md.is_float ? INFINITY : (arm ? (float)(p.sat_var + 1) : (gpu ? 127.0f : (float)p.sat_var));
+    md.x86 = !md.is_float && (p.semantics == LDPC_SEM_X86_SSE || p.semantics == LDPC_SEM_UNIFORM);
+    md.quirk = !md.is_float && p.semantics == LDPC_SEM_X86_SSE && p.algo == LDPC_ALGO_OMS;
+    return md;
 }
 
 // Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table, (G, P) grouping.
@@ -230,21 +273,78 @@ void destroy_impl(ldpc_handle h)
     cudaSetDevice(h->device);
     for (auto& s : h->slot) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-        cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG);
+        cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
     cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos);
-    cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters);
+    cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge);
     free(h->code.pos);
     delete h;
 }
 
+int ensure_debug(ldpc_handle h, size_t frames, int iters)
+{
+    int rc;
+    if ((rc = ensure(h, &h->d_dbg_post, &h->dbg_post_bytes, frames * (size_t)h->code.n * h->elem))) return rc;
+    if ((rc = ensure(h, &h->d_dbg_msgs, &h->dbg_msgs_bytes, frames * (size_t)h->code.m * h->elem))) return rc;
+    h->dbg_frames = frames; h->dbg_iters = iters;
+    return LDPC_OK;
+}
+
 size_t hard_row_bytes(ldpc_handle h) { return h->prm.out_format == LDPC_OUT_PACKED ? (size_t)(h->code.n + 7) / 8 : (size_t)h->code.n; }
+
+// generic engine: interleave (+ clamp) -> decode -> hard decisions; S = storage type of the boundary and of the HBM state
+template <class S>
+int launch_decode_gp(ldpc_handle h, Slot& s, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
+{
+    const ldpc_code_t& c = h->code;
+    const int T = (int)((frames + 31) / 32 * 32);
+    const bool flooding = h->prm.schedule == LDPC_SCHED_FLOODING;
+    int rc;
+    if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * sizeof(S)))) return rc;
+    if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * sizeof(S)))) return rc;
+    if (flooding && (rc = ensure(h, &s.d_LLR0, &s.llr0_bytes, (size_t)c.n * T * sizeof(S)))) return rc;
+    s.T = T;
+    const dim3 blk(32, 8), gn((unsigned)(T / 32), (unsigned)((c.n + 31) / 32)), gm((unsigned)(T / 32), (unsigned)((c.m + 31) / 32));
+    S* V = reinterpret_cast<S*>(s.d_V); S* MSG = reinterpret_cast<S*>(s.d_MSG); S* LLR0 = reinterpret_cast<S*>(s.d_LLR0);
+    gp_interleave_kernel<S><<<gn, blk, 0, st>>>(reinterpret_cast<const S*>(d_llr), V, frames, c.n, T, h->gp_mode.is_float ? 0 : 1, h->gp_mode.lo, h->gp_mode.hi);
+    CU_TRY(h, cudaGetLastError());
+    if (flooding) CU_TRY(h, cudaMemcpyAsync(LLR0, V, (size_t)c.n * T * sizeof(S), cudaMemcpyDeviceToDevice, st));
+    if (iters == 0 && want_debug) CU_TRY(h, cudaMemsetAsync(MSG, 0, (size_t)c.m * T * sizeof(S), st));
+    GpArgs<S> a{};
+    a.V = V; a.MSG = MSG; a.LLR = LLR0; a.pos = h->d_pos; a.cptr = h->d_cptr; a.cedge = h->d_cedge; a.iters_done = nullptr;
+    a.T = T; a.n = c.n; a.m = c.m; a.nb_deg = c.nb_deg;
+    for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { a.deg[i] = c.deg[i]; a.rows[i] = c.rows[i]; }
+    a.iters = iters; a.flooding = flooding; a.et = h->prm.early_term == LDPC_ET_SYNDROME; a.md = h->gp_mode;
+    if (d_iters) {
+        if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (size_t)T))) return rc;
+        a.iters_done = s.d_iters;
+    }
+    gp_decode_kernel<S><<<T / GP_BLOCK + (T % GP_BLOCK ? 1 : 0), GP_BLOCK, 0, st>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    if (h->prm.out_format == LDPC_OUT_PACKED) gp_hard_kernel<S, true><<<gn, blk, 0, st>>>(V, d_hard, frames, c.n, T);
+    else gp_hard_kernel<S, false><<<gn, blk, 0, st>>>(V, d_hard, frames, c.n, T);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 3;
+    if (d_iters && d_iters != s.d_iters) CU_TRY(h, cudaMemcpyAsync(d_iters, s.d_iters, frames, cudaMemcpyDeviceToDevice, st));
+    if (want_debug) {
+        gp_deinterleave_kernel<S><<<gn, blk, 0, st>>>(V, reinterpret_cast<S*>(h->d_dbg_post), frames, c.n, T);
+        gp_deinterleave_kernel<S><<<gm, blk, 0, st>>>(MSG, reinterpret_cast<S*>(h->d_dbg_msgs), frames, c.m, T);
+        CU_TRY(h, cudaGetLastError());
+        h->launches += 2;
+    }
+    return LDPC_OK;
+}
 
 // decode `frames` frames that are already in device memory, on stream st.  For the frame-parallel kernel the slot's V/MSG
 // state is used, `frames` must fit it.
 int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
 {
     const ldpc_code_t& c = h->code;
+    if (h->kernel == 3) {
+        if (h->elem == 4) return launch_decode_gp<float>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        if (h->elem == 2) return launch_decode_gp<int16_t>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        return launch_decode_gp<int8_t>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+    }
     const int et = h->prm.early_term == LDPC_ET_SYNDROME;
     const int lo = lo_rail(h->prm), hi = hi_rail(h->prm);
     if (h->kernel == 2) {
@@ -364,9 +464,24 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     CREATE_TRY(cudaMemcpy(h->d_pos, code->pos, sizeof(uint32_t) * (size_t)code->m, cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc((void**)&h->d_counters, 2 * sizeof(unsigned long long)));
 
-    // kernel selection: the on-chip row-parallel kernel needs the whole state of >= 8 frame pairs per SM in shared memory
-    h->kernel = 1;
-    if (code->n <= 16383 && params->kernel != 1) {
+    // kernel selection.  int16 / float / flooding -> the generic engine; int8 layered -> the on-chip row-parallel kernel when the
+    // whole state of >= 8 frame pairs per SM fits in shared memory, else the frame-parallel kernel
+    const bool generic = params->dtype != LDPC_DTYPE_I8 || params->schedule != LDPC_SCHED_LAYERED || params->kernel == 3;
+    h->elem = params->dtype == LDPC_DTYPE_F32 ? 4 : (params->dtype == LDPC_DTYPE_I16 ? 2 : 1);
+    h->kernel = generic ? 3 : 1;
+    if (generic) {
+        h->gp_mode = make_gp_mode(*params);
+        std::vector<int32_t> cptr((size_t)code->n + 1, 0), cedge((size_t)code->m);
+        for (int e = 0; e < code->m; e++) cptr[code->pos[e] + 1]++;
+        for (int i = 0; i < code->n; i++) cptr[i + 1] += cptr[i];
+        { std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+          for (int e = 0; e < code->m; e++) cedge[fill[code->pos[e]]++] = e; }              // ascending edge order inside a column
+        CREATE_TRY(cudaMalloc((void**)&h->d_cptr, cptr.size() * sizeof(int32_t)));
+        CREATE_TRY(cudaMemcpy(h->d_cptr, cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc((void**)&h->d_cedge, cedge.size() * sizeof(int32_t)));
+        CREATE_TRY(cudaMemcpy(h->d_cedge, cedge.data(), cedge.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (!generic && code->n <= 16383 && params->kernel != 1) {
         RpPlan plan;
         if ((rc = build_rp_plan(h, plan, (size_t)prop.sharedMemPerBlockOptin))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
         h->rp_npad = (code->n + 3) / 4 * 4;
@@ -390,13 +505,13 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMemcpy(h->d_edge_of, plan.edge_of.data(), plan.edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the row-parallel kernel"); }
     } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 16383"); }
-    if (h->kernel == 1 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
+    if (h->kernel != 2 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
 #undef CREATE_TRY
     // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
     // pipeline granularity of decode(): whole waves of the chosen kernel.  H2D, kernel and D2H take about the same time per
     // frame for 576x288 over PCIe Gen5, so the fill/drain of the 3-stage pipeline costs 2 chunks: many small chunks win
     // (measured: 5 chunks 1.17 ms, 10 chunks of one wave each — see profiles/r01_e2e_chunks.txt).  reserved[2] overrides (waves per chunk).
-    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : (size_t)h->sms * 512 * 4;
+    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
     size_t k = h->kernel == 2 ? 1 : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
@@ -412,8 +527,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     switch (what) {
     case LDPC_INFO_KERNEL: *value = h->kernel; break;
     case LDPC_INFO_LEVELS: *value = h->levels; break;
-    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : 16384; break;
-    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : FP_BLOCK * 4; break;
+    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : (h->kernel == 3 ? 0 : 16384); break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : FP_BLOCK * 4); break;
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;
@@ -439,12 +554,7 @@ int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, s
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
     const bool dbg = h->debug;
-    if (dbg) {
-        int rc; size_t have_p = h->dbg_frames_cap * h->code.n, have_m = h->dbg_frames_cap * (size_t)h->code.m;
-        if ((rc = ensure(h, &h->d_dbg_post, &have_p, frames * h->code.n))) return rc;
-        if ((rc = ensure(h, &h->d_dbg_msgs, &have_m, frames * (size_t)h->code.m))) return rc;
-        h->dbg_frames_cap = std::max(h->dbg_frames_cap, frames); h->dbg_frames = frames; h->dbg_iters = iters;
-    }
+    if (dbg) { int rc; if ((rc = ensure_debug(h, frames, iters))) return rc; }
     return launch_decode(h, h->slot[0], (const int8_t*)d_llr, d_hard, frames, iters, d_iters_done, st, dbg);
 }
 
@@ -454,23 +564,19 @@ int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* ha
     if (frames == 0) return LDPC_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     Slot& s = h->slot[slot];
-    const size_t n = h->code.n, hb = hard_row_bytes(h);
+    const size_t n = h->code.n, hb = hard_row_bytes(h), el = (size_t)h->elem;
     int rc;
-    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * n))) return rc;
+    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * n * el))) return rc;
     if ((rc = ensure(h, &s.d_hard, &s.hard_bytes, frames * hb))) return rc;
     uint8_t* d_it = nullptr;
     if (iters_done) {
         if (h->kernel == 2) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
+        else if (h->kernel == 3) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (frames + 31) / 32 * 32))) return rc; d_it = s.d_iters; }
         else { const size_t T = ((frames + 3) / 4 + 31) / 32 * 32; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
     }
-    CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n * el, cudaMemcpyHostToDevice, s.stream));
     const bool dbg = h->debug && slot == 0;
-    if (dbg) {
-        size_t have_p = h->dbg_frames_cap * n, have_m = h->dbg_frames_cap * (size_t)h->code.m;
-        if ((rc = ensure(h, &h->d_dbg_post, &have_p, frames * n))) return rc;
-        if ((rc = ensure(h, &h->d_dbg_msgs, &have_m, frames * (size_t)h->code.m))) return rc;
-        h->dbg_frames_cap = std::max(h->dbg_frames_cap, frames); h->dbg_frames = frames; h->dbg_iters = iters;
-    }
+    if (dbg && (rc = ensure_debug(h, frames, iters))) return rc;
     if ((rc = launch_decode(h, s, s.d_llr, s.d_hard, frames, iters, d_it, s.stream, dbg))) return rc;
     CU_TRY(h, cudaMemcpyAsync(hard, s.d_hard, frames * hb, cudaMemcpyDeviceToHost, s.stream));
     if (iters_done) CU_TRY(h, cudaMemcpyAsync(iters_done, d_it, frames, cudaMemcpyDeviceToHost, s.stream));
@@ -495,7 +601,7 @@ int ldpc_b200_decode(ldpc_handle h, const void* llr, uint8_t* hard, size_t frame
         const size_t cnt = std::min(chunk, frames - f);
         const int slot = h->debug ? 0 : (k % kSlots);
         if (k >= kSlots) CU_TRY(h, cudaStreamSynchronize(h->slot[slot].stream));   // slot buffers are reused
-        rc = ldpc_b200_decode_async(h, slot, (const int8_t*)llr + f * n, hard + f * hb, cnt, iters, iters_done ? iters_done + f : nullptr);
+        rc = ldpc_b200_decode_async(h, slot, (const int8_t*)llr + f * n * (size_t)h->elem, hard + f * hb, cnt, iters, iters_done ? iters_done + f : nullptr);
     }
     int rc2 = ldpc_b200_sync(h, -1);
     return rc ? rc : rc2;
@@ -507,8 +613,8 @@ int ldpc_b200_debug_state(ldpc_handle h, void* posteriors, void* msgs, size_t fr
     if (!h->debug || !h->d_dbg_post || frames > h->dbg_frames) return fail(h, LDPC_ERR_INVALID, "debug_state: enable ldpc_b200_set_debug and decode first (frames <= last decode)");
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaDeviceSynchronize());
-    if (posteriors) CU_TRY(h, cudaMemcpy(posteriors, h->d_dbg_post, frames * h->code.n, cudaMemcpyDeviceToHost));
-    if (msgs) CU_TRY(h, cudaMemcpy(msgs, h->d_dbg_msgs, frames * (size_t)h->code.m, cudaMemcpyDeviceToHost));
+    if (posteriors) CU_TRY(h, cudaMemcpy(posteriors, h->d_dbg_post, frames * (size_t)h->code.n * h->elem, cudaMemcpyDeviceToHost));
+    if (msgs) CU_TRY(h, cudaMemcpy(msgs, h->d_dbg_msgs, frames * (size_t)h->code.m * h->elem, cudaMemcpyDeviceToHost));
     return LDPC_OK;
 }
 
@@ -539,8 +645,11 @@ int ldpc_b200_awgn_device(ldpc_handle h, void* d_llr, size_t frames, float sigma
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
     const size_t total = frames * (size_t)((h->code.n + 3) / 4);
-    awgn_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 1u << 20), 256, 0, st>>>((int8_t*)d_llr, frames, h->code.n, sigma, seed, first_frame,
-                                                                                         (float)h->prm.llr_scale, h->prm.sat_llr);
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 1u << 20);
+    const float scale = (float)h->prm.llr_scale; const int sat = h->prm.sat_llr;
+    if (h->elem == 4) awgn_kernel<float><<<blocks, 256, 0, st>>>((float*)d_llr, frames, h->code.n, sigma, seed, first_frame, scale, sat);
+    else if (h->elem == 2) awgn_kernel<int16_t><<<blocks, 256, 0, st>>>((int16_t*)d_llr, frames, h->code.n, sigma, seed, first_frame, scale, sat);
+    else awgn_kernel<int8_t><<<blocks, 256, 0, st>>>((int8_t*)d_llr, frames, h->code.n, sigma, seed, first_frame, scale, sat);
     CU_TRY(h, cudaGetLastError());
     h->launches += 1;
     return LDPC_OK;
@@ -553,9 +662,9 @@ int ldpc_b200_awgn(ldpc_handle h, void* llr_host, size_t frames, float sigma, ui
     CU_TRY(h, cudaSetDevice(h->device));
     Slot& s = h->slot[0];
     int rc;
-    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * (size_t)h->code.n))) return rc;
+    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * (size_t)h->code.n * h->elem))) return rc;
     if ((rc = ldpc_b200_awgn_device(h, s.d_llr, frames, sigma, seed, first_frame, s.stream))) return rc;
-    CU_TRY(h, cudaMemcpyAsync(llr_host, s.d_llr, frames * (size_t)h->code.n, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(h, cudaMemcpyAsync(llr_host, s.d_llr, frames * (size_t)h->code.n * h->elem, cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(h, cudaStreamSynchronize(s.stream));
     return LDPC_OK;
 }

@@ -20,7 +20,7 @@ static inline int maxi(int a, int b) { return a > b ? a : b; }
 static inline int absi(int a) { return a < 0 ? -a : a; }
 
 typedef struct {
-    int sem, algo, offset, factor_q5, sat_var, sat_msg, et;
+    int sem, algo, offset, factor_q5, sat_var, sat_msg, et, wide, flooding;
     float f1, f2;
 } oparams;
 
@@ -70,7 +70,11 @@ static inline void row_constants(const oparams* p, int min1, int min2, int cls, 
     switch (p->sem) {
     case LDPC_SEM_X86_SSE:
     case LDPC_SEM_UNIFORM:
-        if (p->algo == LDPC_ALGO_NMS) {
+        if (p->algo == LDPC_ALGO_NMS && p->wide) {
+            /* int16 storage (no reference decoder, own definition): the same (min*factor)>>5 without the 16-bit lane wrap and
+             * with the pack saturation at the int16 rail */
+            *c1 = mini((min2 * p->factor_q5) >> 5, 32767); *c2 = mini((min1 * p->factor_q5) >> 5, 32767);
+        } else if (p->algo == LDPC_ALGO_NMS) {
             /* unpack to u16, mullo_epi16, srli 5, packs_epi16  (ref: CDecoder_NMS_fixed_SSE.cpp:196-208) */
             int t2 = ((min2 * p->factor_q5) & 0xFFFF) >> 5, t1 = ((min1 * p->factor_q5) & 0xFFFF) >> 5;
             *c1 = mini(t2, 127); *c2 = mini(t1, 127);
@@ -122,69 +126,92 @@ static int validate(const ldpc_code_t* code, const oparams* p, int wide)
     return 0;
 }
 
-/* decode ONE frame held in int arrays v[n] (in: LLR, out: posterior) and m[M] (out: messages). Returns iterations run. */
-static int decode_frame(const ldpc_code_t* code, const oparams* p, int* v, int* m, int iters, int wide)
+/* rails of the posterior / contribution in the mode (int8: hi is 127 except ARM; wide: +-sat_var) */
+static inline int rail_lo(const oparams* p) { return p->sem == LDPC_SEM_GPU_FIXED ? -128 : -p->sat_var; }
+static inline int rail_hi(const oparams* p) { return (p->sem == LDPC_SEM_ARM_SCALAR || p->wide) ? p->sat_var : 127; }
+
+/* one check row: contributions from (v, m), new messages into m; posteriors written back only when `write_v` (layered). */
+static inline void update_row(const ldpc_code_t* code, const oparams* p, int* v, int* m, int e, int d, int c, int first_iter, int write_v)
 {
     const uint32_t* pos = code->pos;
+    const int wide = p->wide;
     const int x86 = (p->sem == LDPC_SEM_X86_SSE || p->sem == LDPC_SEM_UNIFORM);
     /* running-min initial value: 127 = vSAT_POS_VAR on x86 (ref: CDecoder_OMS_fixed_SSE.cpp:177-178), 0x7F on GPU
      * (ref: CUDA_OMS_SIMD.cu:51-52), vSAT_POS_VAR+1 in the ARM scalar decoder (ref: CDecoder_OMS_fixed_x86.cpp:78-79) */
     const int min_init = (p->sem == LDPC_SEM_ARM_SCALAR) ? p->sat_var + 1 : (p->sem == LDPC_SEM_GPU_FIXED ? 127 : p->sat_var);
     int x[MAXDEG], a[MAXDEG];
+    int min1 = min_init, min2 = min_init, par = 0;
+    for (int j = 0; j < d; j++) {
+        x[j] = contrib(p, v[pos[e + j]], m[e + j], wide);
+        a[j] = magnitude(p, x[j], c);
+        /* (ref: CDecoder_OMS_fixed_SSE.cpp:213-215 / CUDA_OMS_SIMD.cu:168-169) */
+        int old = min1;
+        min1 = mini(min1, a[j]);
+        min2 = mini(min2, maxi(a[j], old));
+        /* x86: sign bit, zero is positive (ref: :209-210). GPU/ARM: vcmpgts4(x,0) / Signe_de_contrib, zero is negative
+         * (ref: CUDA_OMS_SIMD.cu:170, CDecoder_OMS_fixed_x86.cpp:22,91) */
+        par ^= x86 ? (x[j] < 0) : (x[j] > 0);
+    }
+    int c1, c2;
+    row_constants(p, min1, min2, c, first_iter, &c1, &c2);
+    for (int j = 0; j < d; j++) {
+        int mag = (a[j] == min1) ? c1 : c2;
+        int msg, vn;
+        if (x86) {
+            /* sign ^ 0xC0 (odd degree) / 0x40 (even) then _mm_sign_epi8 (ref: CDecoder_OMS_fixed_SSE.cpp:180-190,232-236,243-244) */
+            int negate = par ^ (x[j] < 0) ^ (d & 1);
+            msg = negate ? -mag : mag;
+            int s = x[j] + msg;
+            if (!wide) s = clampi(s, -128, 127);
+            vn = clampi(s, -p->sat_var, wide ? p->sat_var : 127);   /* adds_epi8 then max(min_var) (ref: :58-59,245) */
+        } else if (p->sem == LDPC_SEM_ARM_SCALAR) {
+            int keep = par ^ (x[j] > 0);
+            msg = keep ? mag : -mag;
+            msg = clampi(msg, -p->sat_msg, p->sat_msg);                       /* (ref: CDecoder_OMS_fixed_x86.cpp:101-102) */
+            vn = clampi(x[j] + msg, -p->sat_var, p->sat_var);
+        } else {
+            int keep = par ^ (x[j] > 0);
+            msg = keep ? mag : -mag;                                          /* (ref: CUDA_OMS_SIMD.cu:182-183) */
+            vn = clampi(x[j] + msg, -128, 127);                               /* vaddss4 (ref: :186) */
+        }
+        if (write_v) v[pos[e + j]] = vn;
+        m[e + j] = msg;
+    }
+}
+
+/* decode ONE frame held in int arrays v[n] (in: LLR, out: posterior) and m[M] (out: messages). Returns iterations run.
+ * Layered = every reference decoder.  Flooding has NO reference implementation — own definition, PARITY UNPINNED:
+ * the row update is the mode's own (same rails, magnitudes, sign conventions, constants), applied to every row against the
+ * posteriors of the previous iteration; then every posterior is rebuilt as clamp(llr + sum of its new messages) with a wide
+ * accumulator; the stop criterion is the syndrome of the hard decisions.  llr0[n] is scratch for the clamped channel values. */
+static int decode_frame(const ldpc_code_t* code, const oparams* p, int* v, int* m, int* llr0, int iters)
+{
+    const uint32_t* pos = code->pos;
+    const int wide = p->wide;
     int done = 0;
     memset(m, 0, sizeof(int) * (size_t)code->m);   /* (ref: CDecoder_OMS_fixed_SSE.cpp:129-131); GPU peels iteration 1 instead (CUDA_OMS_SIMD.cu:40-132) */
+    if (p->flooding) for (int i = 0; i < code->n; i++) llr0[i] = v[i] = clampi(v[i], rail_lo(p), rail_hi(p));
     for (int it = 0; it < iters; it++) {
         int e = 0;
         for (int c = 0; c < code->nb_deg; c++) {
             const int d = code->deg[c];
-            for (int r = 0; r < code->rows[c]; r++, e += d) {
-                int min1 = min_init, min2 = min_init, par = 0;
-                for (int j = 0; j < d; j++) {
-                    x[j] = contrib(p, v[pos[e + j]], m[e + j], wide);
-                    a[j] = magnitude(p, x[j], c);
-                    /* (ref: CDecoder_OMS_fixed_SSE.cpp:213-215 / CUDA_OMS_SIMD.cu:168-169) */
-                    int old = min1;
-                    min1 = mini(min1, a[j]);
-                    min2 = mini(min2, maxi(a[j], old));
-                    /* x86: sign bit, zero is positive (ref: :209-210). GPU/ARM: vcmpgts4(x,0) / Signe_de_contrib, zero is negative
-                     * (ref: CUDA_OMS_SIMD.cu:170, CDecoder_OMS_fixed_x86.cpp:22,91) */
-                    par ^= x86 ? (x[j] < 0) : (x[j] > 0);
-                }
-                int c1, c2;
-                row_constants(p, min1, min2, c, it == 0, &c1, &c2);
-                for (int j = 0; j < d; j++) {
-                    int mag = (a[j] == min1) ? c1 : c2;
-                    int msg;
-                    if (x86) {
-                        /* sign ^ 0xC0 (odd degree) / 0x40 (even) then _mm_sign_epi8 (ref: CDecoder_OMS_fixed_SSE.cpp:180-190,232-236,243-244) */
-                        int negate = par ^ (x[j] < 0) ^ (d & 1);
-                        msg = negate ? -mag : mag;
-                        int s = x[j] + msg;
-                        if (!wide) s = clampi(s, -128, 127);
-                        v[pos[e + j]] = clampi(s, -p->sat_var, wide ? p->sat_var : 127);   /* adds_epi8 then max(min_var) (ref: :58-59,245) */
-                    } else if (p->sem == LDPC_SEM_ARM_SCALAR) {
-                        int keep = par ^ (x[j] > 0);
-                        msg = keep ? mag : -mag;
-                        msg = clampi(msg, -p->sat_msg, p->sat_msg);                       /* (ref: CDecoder_OMS_fixed_x86.cpp:101-102) */
-                        v[pos[e + j]] = clampi(x[j] + msg, -p->sat_var, p->sat_var);
-                    } else {
-                        int keep = par ^ (x[j] > 0);
-                        msg = keep ? mag : -mag;                                          /* (ref: CUDA_OMS_SIMD.cu:182-183) */
-                        v[pos[e + j]] = clampi(x[j] + msg, -128, 127);                    /* vaddss4 (ref: :186) */
-                    }
-                    m[e + j] = msg;
-                }
-            }
+            for (int r = 0; r < code->rows[c]; r++, e += d) update_row(code, p, v, m, e, d, c, it == 0, !p->flooding);
+        }
+        if (p->flooding) {
+            for (int i = 0; i < code->n; i++) v[i] = llr0[i];
+            for (int q = 0; q < code->m; q++) v[pos[q]] += m[q];
+            for (int i = 0; i < code->n; i++) v[i] = clampi(v[i], rail_lo(p), rail_hi(p));
         }
         done = it + 1;
         if (p->et == LDPC_ET_SYNDROME) {
-            /* second pass over every row with the updated messages (ref: CDecoder_OMS_fixed_x86.cpp:150-192) */
+            /* layered: second pass over every row with the updated messages (ref: CDecoder_OMS_fixed_x86.cpp:150-192);
+             * flooding: parity of the hard decisions */
             int stop = 1; e = 0;
             for (int c = 0; c < code->nb_deg && stop; c++) {
                 const int d = code->deg[c];
                 for (int r = 0; r < code->rows[c]; r++, e += d) {
                     int par = 0;
-                    for (int j = 0; j < d; j++) par ^= (contrib(p, v[pos[e + j]], m[e + j], wide) > 0);
+                    for (int j = 0; j < d; j++) par ^= p->flooding ? (v[pos[e + j]] > 0) : (contrib(p, v[pos[e + j]], m[e + j], wide) > 0);
                     if (par) { stop = 0; break; }
                 }
             }
@@ -198,19 +225,21 @@ static void load_params(const ldpc_params_t* prm, oparams* p)
 {
     p->sem = prm->semantics; p->algo = prm->algo; p->offset = prm->offset; p->factor_q5 = prm->factor_q5;
     p->sat_var = prm->sat_var; p->sat_msg = prm->sat_msg; p->et = prm->early_term; p->f1 = prm->factor1; p->f2 = prm->factor2;
+    p->wide = 0; p->flooding = prm->schedule == LDPC_SCHED_FLOODING;
 }
 
 static int decode_range(const ldpc_code_t* code, const oparams* p, const void* llr, uint8_t* hard, void* post, void* msgs,
                         uint8_t* iters_done, size_t f0, size_t f1, int iters, int wide)
 {
     const int n = code->n, M = code->m;
-    int* v = (int*)malloc(sizeof(int) * (size_t)(n + M));
+    int* v = (int*)malloc(sizeof(int) * (size_t)(2 * n + M));
     if (!v) return LDPC_ERR_NOMEM;
     int* m = v + n;
+    int* llr0 = m + M;
     for (size_t f = f0; f < f1; f++) {
         if (wide) { const int16_t* q = (const int16_t*)llr + f * n; for (int i = 0; i < n; i++) v[i] = q[i]; }
         else      { const int8_t*  q = (const int8_t*)llr  + f * n; for (int i = 0; i < n; i++) v[i] = q[i]; }
-        int done = decode_frame(code, p, v, m, iters, wide);
+        int done = decode_frame(code, p, v, m, llr0, iters);
         for (int i = 0; i < n; i++) hard[f * n + i] = (uint8_t)(v[i] > 0);   /* (ref: x86/CTools/CTools.cpp:370; GPU_Transpose_uint8.cu:29) */
         if (iters_done) iters_done[f] = (uint8_t)done;
         if (post) {
@@ -232,6 +261,7 @@ int oracle_decode_fixed(const ldpc_code_t* code, const ldpc_params_t* prm, const
     if (!prm || !llr || !hard || (elem_bytes != 1 && elem_bytes != 2) || iters < 0) return LDPC_ERR_INVALID;
     oparams p; load_params(prm, &p);
     const int wide = elem_bytes == 2;
+    p.wide = wide;
     int rc = validate(code, &p, wide);
     if (rc) return rc;
     return decode_range(code, &p, llr, hard, post, msgs, iters_done, 0, frames, iters, wide);
@@ -251,6 +281,7 @@ int oracle_decode_fixed_mt(const ldpc_code_t* code, const ldpc_params_t* prm, co
     if (!prm || !llr || !hard || (elem_bytes != 1 && elem_bytes != 2) || iters < 0) return LDPC_ERR_INVALID;
     oparams p; load_params(prm, &p);
     const int wide = elem_bytes == 2;
+    p.wide = wide;
     int rc = validate(code, &p, wide);
     if (rc) return rc;
     if (threads < 1) threads = 1;
@@ -271,7 +302,7 @@ int oracle_decode_fixed_mt(const ldpc_code_t* code, const ldpc_params_t* prm, co
 }
 
 /* ---------------------------------------------------------------------------------------------------------------------
- * Float normalised min-sum.  NO reference implementation exists (float kernels are declarations only:
+ * Float normalised / offset min-sum.  NO reference implementation exists (float kernels are declarations only:
  * gpu_fixed/decoder_template/GPU_Scheduled_functions.h:31-34,54-61; x86 float decode is an empty stub:
  * x86/CDecoder/template/CDecoder_fixed_SSE.cpp:35-40).  This is the library's own definition — PARITY UNPINNED.
  * Convention kept from the fixed-point decoders: bit 1 <=> LLR > 0, edge keeps a positive sign iff the XOR of the other
@@ -284,6 +315,8 @@ static int decode_frame_float(const ldpc_code_t* code, const ldpc_params_t* prm,
     const uint32_t* pos = code->pos;
     const float f1 = prm->factor1, f2 = (prm->algo == LDPC_ALGO_2NMS) ? prm->factor2 : prm->factor1;
     const int flooding = prm->schedule == LDPC_SCHED_FLOODING;
+    /* float OMS: the fixed-point offset expressed in channel units (offset / llr_scale, exact for power-of-two scales) */
+    const float off = (float)prm->offset / (float)(prm->llr_scale > 0 ? prm->llr_scale : 1);
     int done = 0;
     for (int i = 0; i < n; i++) post[i] = llr[i];
     for (int e = 0; e < M; e++) { c2v[e] = 0.0f; v2c[e] = llr[pos[e]]; }
@@ -302,7 +335,9 @@ static int decode_frame_float(const ldpc_code_t* code, const ldpc_params_t* prm,
                     min2 = fminf(min2, fmaxf(a[j], old));
                     par ^= (x[j] > 0.0f);
                 }
-                volatile float c1 = min2 * f2, c2 = min1 * f1;   /* volatile: one rounding each, no contraction */
+                volatile float c1, c2;                           /* volatile: one rounding each, no contraction */
+                if (prm->algo == LDPC_ALGO_OMS) { c1 = fmaxf(min2 - off, 0.0f); c2 = fmaxf(min1 - off, 0.0f); }
+                else { c1 = min2 * f2; c2 = min1 * f1; }
                 for (int j = 0; j < d; j++) {
                     float mag = (a[j] == min1) ? c1 : c2;
                     int keep = par ^ (x[j] > 0.0f);
@@ -334,11 +369,11 @@ static int decode_frame_float(const ldpc_code_t* code, const ldpc_params_t* prm,
     return done;
 }
 
-int oracle_decode_float(const ldpc_code_t* code, const ldpc_params_t* prm, const float* llr, uint8_t* hard, float* post,
+int oracle_decode_float(const ldpc_code_t* code, const ldpc_params_t* prm, const float* llr, uint8_t* hard, float* post, float* msgs,
                         uint8_t* iters_done, size_t frames, int iters)
 {
     if (!code || !prm || !llr || !hard || iters < 0) return LDPC_ERR_INVALID;
-    if (prm->algo != LDPC_ALGO_NMS && prm->algo != LDPC_ALGO_2NMS && prm->algo != LDPC_ALGO_MS) return LDPC_ERR_UNSUPPORTED;
+    if (prm->algo < LDPC_ALGO_MS || prm->algo > LDPC_ALGO_2NMS) return LDPC_ERR_UNSUPPORTED;
     ldpc_params_t q = *prm;
     if (q.algo == LDPC_ALGO_MS) { q.factor1 = 1.0f; q.factor2 = 1.0f; }
     const int n = code->n, M = code->m;
@@ -349,6 +384,7 @@ int oracle_decode_float(const ldpc_code_t* code, const ldpc_params_t* prm, const
         int done = decode_frame_float(code, &q, llr + f * n, p, c2v, v2c, iters);
         for (int i = 0; i < n; i++) hard[f * n + i] = (uint8_t)(p[i] > 0.0f);
         if (post) memcpy(post + f * n, p, sizeof(float) * (size_t)n);
+        if (msgs) memcpy(msgs + f * (size_t)M, c2v, sizeof(float) * (size_t)M);
         if (iters_done) iters_done[f] = (uint8_t)done;
     }
     free(buf);

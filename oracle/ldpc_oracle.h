@@ -19,15 +19,17 @@
 extern "C" {
 #endif
 
-/* fixed-point layered decoder, all semantics modes.  llr/hard/post/msgs are frame-major; elem_bytes = 1 (int8) or 2 (int16)
+/* fixed-point decoder, all semantics modes; prm->schedule selects layered (every reference decoder) or flooding (own
+ * definition, unpinned: no reference decoder floods).  llr/hard/post/msgs are frame-major; elem_bytes = 1 (int8) or 2 (int16)
  * selects the width of llr/post/msgs storage.  post, msgs, iters_done nullable.  Returns 0 or LDPC_ERR_*. */
 int oracle_decode_fixed(const ldpc_code_t* code, const ldpc_params_t* prm,
                         const void* llr, uint8_t* hard, void* post, void* msgs, uint8_t* iters_done,
                         size_t frames, int iters, int elem_bytes);
 
-/* float normalised min-sum, flooding or layered, optional syndrome early termination (own definition; unpinned) */
+/* float min-sum (MS / offset / normalised / 2-factor normalised), flooding or layered, optional syndrome early termination
+ * (own definition; unpinned).  post [frames][n], msgs [frames][m] (check-to-variable), iters_done nullable. */
 int oracle_decode_float(const ldpc_code_t* code, const ldpc_params_t* prm,
-                        const float* llr, uint8_t* hard, float* post, uint8_t* iters_done,
+                        const float* llr, uint8_t* hard, float* post, float* msgs, uint8_t* iters_done,
                         size_t frames, int iters);
 
 /* q = clamp((int)(scale*y), -sat, sat)  (ref: code/x86/CFixPointConversion/CFastFixConversion.cpp:55-65) */

@@ -39,7 +39,7 @@ def oracle():
         L.oracle_decode_fixed_mt.restype = i32
         L.oracle_decode_fixed_mt.argtypes = [C.POINTER(CodeT), C.POINTER(ParamsT), vp, vp, sz, i32, i32, i32]
         L.oracle_decode_float.restype = i32
-        L.oracle_decode_float.argtypes = [C.POINTER(CodeT), C.POINTER(ParamsT), vp, vp, vp, vp, sz, i32]
+        L.oracle_decode_float.argtypes = [C.POINTER(CodeT), C.POINTER(ParamsT), vp, vp, vp, vp, vp, sz, i32]
         L.oracle_quantize.restype = None
         L.oracle_quantize.argtypes = [vp, vp, sz, i32, i32]
         L.oracle_pack_bits.restype = None
@@ -63,6 +63,19 @@ def oracle_decode(code: Code, prm: ParamsT, llr: np.ndarray, iters: int, want_st
                                       it.ctypes.data if want_iters else None, F, iters, eb)
     if rc:
         raise RuntimeError(f"oracle_decode_fixed -> {rc}")
+    return dict(hard=hard, post=post, msgs=msgs, iters=it)
+
+
+def oracle_decode_float(code: Code, prm: ParamsT, llr: np.ndarray, iters: int):
+    """Float min-sum of the CPU restatement (own definition, unpinned): dict(hard, post, msgs, iters)."""
+    llr = np.ascontiguousarray(llr, np.float32)
+    F = llr.shape[0]
+    hard = np.empty((F, code.n), np.uint8); post = np.empty((F, code.n), np.float32); msgs = np.empty((F, code.m), np.float32)
+    it = np.empty(F, np.uint8)
+    c = code.c_struct()
+    rc = oracle().oracle_decode_float(C.byref(c), C.byref(prm), llr.ctypes.data, hard.ctypes.data, post.ctypes.data, msgs.ctypes.data, it.ctypes.data, F, iters)
+    if rc:
+        raise RuntimeError(f"oracle_decode_float -> {rc}")
     return dict(hard=hard, post=post, msgs=msgs, iters=it)
 
 

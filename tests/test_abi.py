@@ -94,7 +94,8 @@ def test_invalid_configurations_are_rejected(built):
     c = pkg.Code.load("576x288")
     cs = c.c_struct()
     h = C.c_void_p()
-    for kw in [dict(semantics="X86_SSE", algo="MS"), dict(sat_var=100), dict(dtype=2), dict(schedule=1), dict(factor_q5=999), dict(early_term=7)]:
+    for kw in [dict(semantics="X86_SSE", algo="MS"), dict(sat_var=100), dict(dtype=7), dict(schedule=3), dict(factor_q5=999), dict(early_term=7),
+               dict(dtype=1, semantics="X86_SSE"), dict(dtype=2, kernel=2), dict(schedule=1, kernel=1), dict(kernel=9)]:
         prm = pkg.default_params(**kw)
         rc = pkg.lib().ldpc_b200_create(C.byref(h), C.byref(cs), C.byref(prm), 0, 1024)
         assert rc in (pkg.ERR_INVALID, pkg.ERR_UNSUPPORTED), kw

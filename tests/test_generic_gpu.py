@@ -1,0 +1,123 @@
+"""GPU suite, generic engine (kernel 3: one frame per thread, fp32 arithmetic): int16 storage, float min-sum, the flooding
+schedule — and int8 layered in all four reference semantics, which pins this engine to the reference-checked oracle.
+Integer modes are bit-exact (hard decisions, posteriors, messages, iteration counts).  The float mode issues the oracle's
+operations in the oracle's order, so it is compared bit-for-bit too; the stated tolerance of the float path is therefore 0 ulp
+against oracle/ldpc_oracle.c (which is this project's own definition: no float decoder exists in the reference — parity unpinned)."""
+import numpy as np
+import pytest
+
+import ldpcgputegra_b200 as pkg
+from _helpers import Code, oracle_decode, oracle_decode_float, awgn_llr, stress_llr
+
+pytestmark = pytest.mark.gpu
+
+COMBOS = [("X86_SSE", "OMS"), ("X86_SSE", "NMS"), ("UNIFORM", "OMS"), ("UNIFORM", "NMS"), ("ARM_SCALAR", "OMS"),
+          ("GPU_FIXED", "MS"), ("GPU_FIXED", "OMS"), ("GPU_FIXED", "NMS"), ("GPU_FIXED", "2NMS")]
+
+
+def gpu_decode(code, llr, iters, **kw):
+    dec = pkg.CGPUDecoder(code, nb_frames=max(llr.shape[0], 1), device=0, **kw)
+    dec.set_debug(True)
+    hard, it = dec.decode(llr, iters, want_iters=True)
+    post, msgs = dec.debug_state(llr.shape[0])
+    k, prm = dec.info(pkg.INFO_KERNEL), dec.params
+    dec.close()
+    assert k == 3
+    return dict(hard=hard, post=post, msgs=msgs, iters=it, prm=prm)
+
+
+def assert_same(g, o, what, iters=True):
+    for key in ("hard", "post", "msgs") + (("iters",) if iters else ()):
+        assert g[key].dtype == o[key].dtype and np.array_equal(g[key], o[key]), f"{what}: {key} differs in {(g[key] != o[key]).sum()} entries"
+
+
+def float_llr(code, frames, ebn0, seed):
+    """unquantised channel values y = -1 + sigma*n (norm_channel = false, ref: code/x86/main_p.cpp:124)"""
+    rate = (code.n - code.n_checks) / code.n
+    sigma = np.sqrt(10.0 ** (-(ebn0 + 10.0 * np.log10(rate)) / 10.0) / 2.0)
+    rng = np.random.Generator(np.random.Philox(seed))
+    return (-1.0 + sigma * rng.standard_normal((frames, code.n))).astype(np.float32)
+
+
+@pytest.mark.parametrize("sem,algo", COMBOS)
+def test_int8_layered_pins_generic_engine(code576, sem, algo):
+    llr = np.concatenate([awgn_llr(code576, 200, 2.0, 141), stress_llr(code576, 150, 143), stress_llr(code576, 101, 144, full_range=True)])
+    for iters in (1, 10):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=3)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"{sem}/{algo}/I{iters}")
+
+
+@pytest.mark.parametrize("sem,algo", COMBOS)
+def test_int8_flooding(code576, sem, algo):
+    llr = np.concatenate([awgn_llr(code576, 200, 2.0, 151), stress_llr(code576, 133, 153, full_range=(sem == "GPU_FIXED"))])
+    for iters, et in ((1, 0), (10, 0), (30, 1)):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, schedule="FLOODING", early_term=et)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"flooding {sem}/{algo}/I{iters}/et{et}")
+    assert g["iters"].min() < 30
+
+
+@pytest.mark.parametrize("schedule", ["LAYERED", "FLOODING"])
+@pytest.mark.parametrize("kw", [dict(semantics="ARM_SCALAR", algo="OMS", sat_var=32767, sat_msg=8191, offset=16),
+                                dict(semantics="ARM_SCALAR", algo="OMS", sat_var=2047, sat_msg=511, offset=8),
+                                dict(semantics="UNIFORM", algo="OMS", sat_var=32767, sat_msg=4095, offset=16),
+                                dict(semantics="UNIFORM", algo="NMS", sat_var=8191, sat_msg=2047, factor_q5=29)])
+def test_int16(code576, schedule, kw):
+    q8 = np.concatenate([awgn_llr(code576, 200, 1.5, 161), stress_llr(code576, 120, 163)]).astype(np.int16)
+    llr = (q8 * 16 + (np.arange(q8.size).reshape(q8.shape) % 13 - 6)).astype(np.int16)     # 16x finer grid, not multiples of 16
+    llr[5] = np.clip(llr[5].astype(np.int32) * 40, -32768, 32767).astype(np.int16)         # drives the rails
+    for iters, et in ((2, 0), (10, 0), (25, 1)):
+        g = gpu_decode(code576, llr, iters, dtype="I16", schedule=schedule, early_term=et, **kw)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"int16 {schedule} {kw} I{iters} et{et}")
+
+
+@pytest.mark.parametrize("schedule", ["FLOODING", "LAYERED"])
+@pytest.mark.parametrize("kw", [dict(algo="NMS", factor1=0.75), dict(algo="2NMS", factor1=0.75, factor2=0.875), dict(algo="MS"),
+                                dict(algo="OMS", offset=1), dict(algo="NMS", factor1=0.8125)])
+def test_float_min_sum(code576, schedule, kw):
+    llr = np.concatenate([float_llr(code576, 150, 2.0, 171), float_llr(code576, 100, 0.5, 172), float_llr(code576, 51, 4.0, 173)])
+    for iters, et in ((1, 0), (10, 0), (40, 1)):
+        g = gpu_decode(code576, llr, iters, dtype="F32", schedule=schedule, early_term=et, **kw)
+        o = oracle_decode_float(code576, g["prm"], llr, iters)
+        # tolerance: 0 (same operations in the same order); hard decisions identical
+        assert_same(g, o, f"float {schedule} {kw} I{iters} et{et}")
+    assert g["iters"].min() < 40
+
+
+@pytest.mark.parametrize("name", ["1944x972", "2048x384", "1200x600", "200x100"])
+def test_generic_engine_other_codes(built, name):
+    """degree 32 rows (2048x384: the run-time-degree path), column degree up to 15 (1200x600), N % 32 != 0 (200x100)"""
+    code = Code.load(name)
+    llr8 = awgn_llr(code, 70, 2.5, 181)
+    g = gpu_decode(code, llr8, 5, algo="OMS", semantics="X86_SSE", kernel=3)
+    assert_same(g, oracle_decode(code, g["prm"], llr8, 5), name + " int8 layered")
+    g = gpu_decode(code, llr8, 5, algo="NMS", semantics="UNIFORM", schedule="FLOODING")
+    assert_same(g, oracle_decode(code, g["prm"], llr8, 5), name + " int8 flooding")
+    y = float_llr(code, 70, 2.5, 182)
+    g = gpu_decode(code, y, 6, dtype="F32", algo="NMS", schedule="FLOODING", early_term=1)
+    assert_same(g, oracle_decode_float(code, g["prm"], y, 6), name + " float flooding")
+
+
+def test_generic_ragged_packed_and_device_channel(code576):
+    y = float_llr(code576, 45, 3.0, 191)
+    for frames in (0, 1, 31, 45):
+        dec = pkg.CGPUDecoder(code576, nb_frames=64, device=0, dtype="F32", algo="NMS", schedule="FLOODING", out_format=1)
+        packed = dec.decode(y[:frames], 8)
+        ref = oracle_decode_float(code576, dec.params, y[:frames], 8)["hard"]
+        assert np.array_equal(np.unpackbits(packed, axis=1, bitorder="little")[:, :code576.n] if frames else packed.reshape(0, code576.n), ref)
+        dec.close()
+    # the on-device channel writes the handle's dtype; same (seed, frame) -> same noise whatever the dtype
+    d8 = pkg.CGPUDecoder(code576, nb_frames=256, device=0)
+    df = pkg.CGPUDecoder(code576, nb_frames=256, device=0, dtype="F32", algo="NMS", schedule="FLOODING")
+    sigma = pkg.sigma_for(2.0, 0.5)
+    q, yf = d8.awgn(256, sigma, seed=5), df.awgn(256, sigma, seed=5)
+    assert yf.dtype == np.float32 and np.array_equal(np.clip(np.trunc(8.0 * yf), -31, 31).astype(np.int8), q)
+    hard = df.decode(yf, 10)
+    assert np.array_equal(hard, oracle_decode_float(code576, df.params, yf, 10)["hard"])
+    d8.close(); df.close()
+
+
+def test_unsupported_combinations_fail_loudly(code576):
+    for kw in [dict(dtype="I16", semantics="X86_SSE"), dict(dtype="I16", semantics="GPU_FIXED"), dict(dtype="F32", kernel=2),
+               dict(schedule="FLOODING", kernel=1), dict(dtype="I16", semantics="UNIFORM", sat_var=40000)]:
+        with pytest.raises(pkg.LdpcError):
+            pkg.CGPUDecoder(code576, nb_frames=64, device=0, **kw)

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from _helpers import (Code, default_params, oracle_decode, oracle_quantize, oracle_pack, awgn_llr, stress_llr,
+from _helpers import (Code, default_params, oracle_decode, oracle_decode_float, oracle_quantize, oracle_pack, awgn_llr, stress_llr,
                       ref_x86, ref_x86_decode, ref_arm, ref_arm_decode, ROOT)
 
 GOLD = ROOT / "tests" / "golden"
@@ -107,3 +107,32 @@ def test_all_zero_codeword_decodes_at_high_snr(code576):
     for sem, algo in [("X86_SSE", "OMS"), ("X86_SSE", "NMS"), ("GPU_FIXED", "MS"), ("GPU_FIXED", "2NMS"), ("ARM_SCALAR", "OMS")]:
         o = oracle_decode(code576, default_params(algo=algo, semantics=sem), llr, 10)
         assert not o["hard"].any(), (sem, algo)
+
+
+def test_own_definitions_flooding_int16_float_behave(code576):
+    """No reference decoder floods, stores int16 or computes in float: these oracle modes are this project's own
+    definitions (parity unpinned).  What can be checked on the CPU: they decode, they agree with the pinned int8 layered decoder
+    where they must, and early termination only ever shortens."""
+    llr = awgn_llr(code576, 200, 3.0, 61)
+    lay = oracle_decode(code576, default_params(algo="OMS", semantics="UNIFORM"), llr, 10)
+    # int16 storage with int8 rails and int8 inputs is the int8 decoder
+    w = oracle_decode(code576, default_params(algo="OMS", semantics="UNIFORM", dtype=1, sat_var=127), llr.astype(np.int16), 10)
+    assert np.array_equal(w["post"], lay["post"].astype(np.int16)) and np.array_equal(w["hard"], lay["hard"])
+    # flooding needs more iterations than layered but converges to the same codeword at 3 dB
+    flo = oracle_decode(code576, default_params(algo="OMS", semantics="UNIFORM", schedule=1), llr, 30)
+    assert (flo["hard"].any(axis=1) == lay["hard"].any(axis=1)).mean() > 0.97
+    fl10 = oracle_decode(code576, default_params(algo="OMS", semantics="UNIFORM", schedule=1), llr, 10)
+    assert fl10["hard"].any(axis=1).sum() >= flo["hard"].any(axis=1).sum()
+    et = oracle_decode(code576, default_params(algo="OMS", semantics="UNIFORM", schedule=1, early_term=1), llr, 30)
+    assert et["iters"].max() <= 30 and et["iters"].min() < 30
+    conv = et["iters"] < 30
+    assert not et["hard"][conv].any()                      # frames that stopped early satisfy every check: the all-zero codeword here
+    # float: unquantised values of the same noise decode at least as well as the 6-bit quantised ones
+    rng = np.random.Generator(np.random.Philox(61))
+    y = (-1.0 + 0.7079 * rng.standard_normal((200, code576.n))).astype(np.float32)
+    for sched in (0, 1):
+        f = oracle_decode_float(code576, default_params(algo="NMS", dtype=2, schedule=sched, early_term=1), y, 40)
+        assert f["hard"].any(axis=1).mean() < 0.05 and f["iters"].min() < 40
+        assert not f["hard"][f["iters"] < 40].any()
+    fo = oracle_decode_float(code576, default_params(algo="OMS", dtype=2, schedule=0), y, 10)
+    assert fo["hard"].any(axis=1).mean() < 0.05
