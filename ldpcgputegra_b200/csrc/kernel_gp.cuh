@@ -21,7 +21,7 @@
 namespace ldpcb200 {
 
 #define GP_BLOCK 128
-#define GP_MAXDEG 64
+#define GP_MAXDEG 4096   // run-time-degree rows keep nothing per edge in registers
 
 struct GpMode {
     int sem;            // ldpc_semantics_t (ignored when is_float)
@@ -107,26 +107,20 @@ __device__ __forceinline__ void gp_constants(const GpMode& md, float min1, float
     c2 = fminf(fmaxf(min1 - md.off, 0.0f), md.sat_msg);
 }
 
-// One check row for one frame.  WRITE_V = layered (posteriors updated in place).  x[] / a[] are register arrays when D is a
-// compile-time constant (DD > 0) and local-memory arrays of GP_MAXDEG otherwise.
-template <class S, int DD, bool WRITE_V>
-__device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int Drt, int cls, bool first)
+// One check row for one frame, degree known at compile time: contributions stay in registers.  WRITE_V = layered (posteriors
+// updated in place).
+template <class S, int D, bool WRITE_V>
+__device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int cls, bool first)
 {
     const GpMode& md = A.md;
-    constexpr int CAP = DD > 0 ? DD : GP_MAXDEG;
-    const int D = DD > 0 ? DD : Drt;
-    float x[CAP], a[CAP];
-    uint32_t idx[CAP];
+    float x[D], a[D];
+    uint32_t idx[D];
     float min1 = md.min_init, min2 = md.min_init;
     int par = 0;
 #pragma unroll
-    for (int j = 0; j < CAP; j++) {
-        if (DD == 0 && j >= D) break;
-        idx[j] = __ldg(A.pos + e + j);
-    }
+    for (int j = 0; j < D; j++) idx[j] = __ldg(A.pos + e + j);
 #pragma unroll
-    for (int j = 0; j < CAP; j++) {
-        if (DD == 0 && j >= D) break;
+    for (int j = 0; j < D; j++) {
         const float v = GpIO<S>::ld(A.V + (size_t)idx[j] * A.T + t);
         const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
         float xx = __fsub_rn(v, m);
@@ -143,8 +137,7 @@ __device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int 
     gp_constants(md, min1, min2, cls, first, c1, c2);
     const int k = md.x86 ? (D & 1) : 1;       // negate = par ^ flag_j ^ k  (x86: degree parity; others: keep = par ^ pos_j)
 #pragma unroll
-    for (int j = 0; j < CAP; j++) {
-        if (DD == 0 && j >= D) break;
+    for (int j = 0; j < D; j++) {
         const float mag = (a[j] == min1) ? c1 : c2;
         const int flag = md.x86 ? (x[j] < 0.0f) : (x[j] > 0.0f);
         const float msg = (par ^ flag ^ k) ? -mag : mag;
@@ -157,17 +150,59 @@ __device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int 
     }
 }
 
+// run-time degree (rows wider than 8: 2048x384 has degree 32, DVB-S2 rate 1/9 degree 27): two passes, the contributions are
+// recomputed from memory in the second one (L1/L2 hits) instead of being parked in local memory
+template <class S, bool WRITE_V>
+__device__ __noinline__ void gp_row_rt(const GpArgs<S>& A, int t, size_t e, int D, int cls, bool first)
+{
+    const GpMode& md = A.md;
+    float min1 = md.min_init, min2 = md.min_init;
+    int par = 0;
+#pragma unroll 1
+    for (int j = 0; j < D; j++) {
+        const float v = GpIO<S>::ld(A.V + (size_t)__ldg(A.pos + e + j) * A.T + t);
+        const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
+        float xx = __fsub_rn(v, m);
+        if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
+        const float aa = gp_magnitude(md, xx, cls);
+        const float old = min1;
+        min1 = fminf(min1, aa);
+        min2 = fminf(min2, fmaxf(aa, old));
+        par ^= md.x86 ? (xx < 0.0f) : (xx > 0.0f);
+    }
+    float c1, c2;
+    gp_constants(md, min1, min2, cls, first, c1, c2);
+    const int k = md.x86 ? (D & 1) : 1;
+#pragma unroll 1
+    for (int j = 0; j < D; j++) {
+        const size_t vi = (size_t)__ldg(A.pos + e + j) * A.T + t;
+        const float v = GpIO<S>::ld(A.V + vi);
+        const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
+        float xx = __fsub_rn(v, m);
+        if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
+        const float mag = (gp_magnitude(md, xx, cls) == min1) ? c1 : c2;
+        const int flag = md.x86 ? (xx < 0.0f) : (xx > 0.0f);
+        const float msg = (par ^ flag ^ k) ? -mag : mag;
+        GpIO<S>::st(A.MSG + (e + j) * A.T + t, msg);
+        if (WRITE_V) {
+            float vn = __fadd_rn(xx, msg);
+            if (!md.is_float) vn = gp_clamp(vn, md.lo, md.hi);
+            GpIO<S>::st(A.V + vi, vn);
+        }
+    }
+}
+
 template <class S, bool WRITE_V>
 __device__ __forceinline__ void gp_all_rows(const GpArgs<S>& A, int t, bool first)
 {
     size_t e = 0;
     for (int c = 0; c < A.nb_deg; c++) {
         const int D = A.deg[c], R = A.rows[c];
-#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V>(A, t, e, DD, c, first); break;
+#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V>(A, t, e, c, first); break;
         switch (D) {
             GP_CASE(3) GP_CASE(4) GP_CASE(5) GP_CASE(6) GP_CASE(7) GP_CASE(8)
         default:
-            for (int r = 0; r < R; r++, e += D) gp_row<S, 0, WRITE_V>(A, t, e, D, c, first);
+            for (int r = 0; r < R; r++, e += D) gp_row_rt<S, WRITE_V>(A, t, e, D, c, first);
         }
 #undef GP_CASE
     }
@@ -211,7 +246,7 @@ __device__ __forceinline__ bool gp_syndrome_ok(const GpArgs<S>& A, int t)
 }
 
 template <class S>
-__global__ void __launch_bounds__(GP_BLOCK) gp_decode_kernel(const __grid_constant__ GpArgs<S> A)
+__global__ void __launch_bounds__(GP_BLOCK, 8) gp_decode_kernel(const __grid_constant__ GpArgs<S> A)
 {
     const int t = blockIdx.x * GP_BLOCK + threadIdx.x;
     if (t >= A.T) return;

@@ -35,7 +35,13 @@ struct RpStep {         // read by the kernel as one 128-bit load (first four wo
 };
 static_assert(sizeof(RpStep) == 32, "RpStep must stay 32 bytes");
 
-struct RpRun { int32_t first, count, variant, quirk; };
+struct RpRun {
+    int32_t first, count, variant, quirk;     // consecutive steps sharing one instantiation; quirk = degree class >= 1
+    uint32_t msg_off0;                        // msg_off of the first step; step s of the run starts at msg_off0 + s * stride * deg
+    uint32_t syncmask;                        // bit s = a new level starts at step s of the run (count <= 32)
+    uint32_t pad[2];
+};
+static_assert(sizeof(RpRun) == 32, "RpRun must stay 32 bytes");
 
 struct RpArgs {
     const int8_t* llr;        // [frames][n] frame-major
@@ -53,6 +59,7 @@ struct RpArgs {
     int n_pad;                // U length in words (multiple of 4)
     int m_elems;              // padded message elements per pair (multiple of 4)
     int G, P;                 // warps per group, pairs per full group
+    int static_nrows;         // > 0: every step has this many rows and P * nrows <= 32 * G — lane t owns (pair t / nrows, row t % nrows) for the whole decode
     int groups;               // groups per CTA
     int slots;                // pair slots per CTA (the last group may own fewer than P)
     int iters;
@@ -169,6 +176,45 @@ __device__ __forceinline__ void rp_run(const RpCtx& c, int first, int count, int
             else rp_row_generic<SEM, ALGO, FIRST, ET, Q>(ub, ub + c.ms_off + 4u * e, c.idx_s + 2u * e, (int)(sd.x & 0xFFFFu), (int)(sd.y & 0xFFFFu), K, msg_c, keep);
         }
     }
+}
+
+// Static plan (all steps have the same number of rows and a full group carries at most one task per lane, e.g. 576x288:
+// 4 pairs x 24 rows on 3 warps): a lane keeps its (pair, row slot) for the whole decode, so a step costs nothing but the
+// row itself — no descriptor load, no task -> (pair, row) arithmetic, addresses advance by a compile-time constant.
+// (profiles/r01_ncu_rp_v3_g34.txt: 32.9 warp instructions per warp-edge-update against ~22 in the row body.)
+struct RpLane { uint32_t ub, ms_lane, ix_lane, keep; bool active; };
+
+template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void rp_run_static(const RpCtx& c, const RpRun& r, const RpLane& L, const RowConsts& K)
+{
+    const h2 msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && FIRST && r.quirk) ? K.one : K.msg;
+    uint32_t mask = r.syncmask, msa = L.ms_lane + 4u * r.msg_off0, ixa = L.ix_lane + 2u * r.msg_off0;
+    for (int s = 0; s < r.count; s++, mask >>= 1, msa += 4u * NR * D, ixa += 2u * NR * D) {
+        if (mask & 1u) group_sync(c.G, c.bar);
+        if (L.active) rp_row<SEM, ALGO, D, NR, FIRST, ET, Q>(L.ub, msa, ixa, K, msg_c, L.keep);
+    }
+}
+
+template <int SEM, int ALGO, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void rp_dispatch_static(const RpCtx& c, const RpRun& r, const RpLane& L, const RowConsts& K)
+{
+#define RP_CASE(ID, DD, NN) case ID: rp_run_static<SEM, ALGO, DD, NN, FIRST, ET, Q>(c, r, L, K); break;
+    switch (r.variant) {
+        RP_CASE(1, 6, 24) RP_CASE(2, 6, 32) RP_CASE(3, 7, 24) RP_CASE(4, 7, 32) RP_CASE(5, 8, 24) RP_CASE(6, 8, 32)
+    }
+#undef RP_CASE
+}
+
+template <int SEM, int ALGO, bool FIRST, bool ET>
+__device__ __forceinline__ void rp_iteration_static(const RpCtx& c, uint32_t runs_s, int nruns, const RpLane& L, const RowConsts& K)
+{
+    for (int i = 0; i < nruns; i++) {
+        const uint4 a = lds_u128(runs_s + 32u * i), b = lds_u128(runs_s + 32u * i + 16u);
+        RpRun r; r.first = (int)a.x; r.count = (int)a.y; r.variant = (int)a.z; r.quirk = (int)a.w; r.msg_off0 = b.x; r.syncmask = b.y;
+        if (SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && r.quirk) rp_dispatch_static<SEM, ALGO, FIRST, ET, true>(c, r, L, K);
+        else rp_dispatch_static<SEM, ALGO, FIRST, ET, false>(c, r, L, K);
+    }
+    group_sync(c.G, c.bar);
 }
 
 template <int SEM, int ALGO, bool FIRST, bool ET, bool Q>
@@ -327,7 +373,7 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
 
     for (int i = threadIdx.x; i < A.nsteps * (int)(sizeof(RpStep) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(steps)[i] = reinterpret_cast<const uint32_t*>(A.steps)[i];
-    for (int i = threadIdx.x; i < A.nruns * 4; i += blockDim.x)
+    for (int i = threadIdx.x; i < A.nruns * (int)(sizeof(RpRun) / 4); i += blockDim.x)
         reinterpret_cast<int32_t*>(runs)[i] = reinterpret_cast<const int32_t*>(A.runs)[i];
     for (int i = threadIdx.x; i < A.m_elems; i += blockDim.x) idx[i] = A.idx_t[i];
     __syncthreads();
@@ -359,10 +405,19 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
             if (ET && lane == 0) { gflags[2 * p] = 0u; gflags[2 * p + 1] = 0u; }
         }
         group_sync(c.G, c.bar);
+        RpLane L;                                          // static plan: this lane's (pair, row slot) for the whole decode
+        const bool stat = A.static_nrows > 0;
+        {
+            const uint32_t lp = stat ? (uint32_t)c.gl / (uint32_t)A.static_nrows : 0u, lz = (uint32_t)c.gl - lp * (uint32_t)A.static_nrows;
+            L.active = stat && (int)lp < valid;
+            L.ub = c.state_s + lp * c.pair_bytes; L.ms_lane = L.ub + c.ms_off + 4u * lz; L.ix_lane = c.idx_s + 2u * lz; L.keep = 0u;
+        }
+        const uint32_t runs_s = smem_u32(runs);
         int it = 0;
         uint32_t done_lo = 0u, done_hi = 0u;               // ET bookkeeping of pair gl lives in lane gl of the group
         if (A.iters > 0) {
-            rp_iteration<SEM, ALGO, true, ET>(c, runs, A.nruns, valid, K);
+            if (stat) rp_iteration_static<SEM, ALGO, true, ET>(c, runs_s, A.nruns, L, K);
+            else rp_iteration<SEM, ALGO, true, ET>(c, runs, A.nruns, valid, K);
             it = 1;
             while (it < A.iters) {
                 if (ET) {
@@ -381,8 +436,10 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
                     group_sync(c.G, c.bar);
                     if (c.gl < valid) gflags[2 * c.gl] = 0u;       // cleared for the next syndrome pass (ordered by the barriers of the iteration)
                     if (!running) break;
+                    if (stat && L.active) L.keep = lds_u32(c.flags_s + 8u * ((uint32_t)c.gl / (uint32_t)A.static_nrows) + 4u);
                 }
-                rp_iteration<SEM, ALGO, false, ET>(c, runs, A.nruns, valid, K);
+                if (stat) rp_iteration_static<SEM, ALGO, false, ET>(c, runs_s, A.nruns, L, K);
+                else rp_iteration<SEM, ALGO, false, ET>(c, runs, A.nruns, valid, K);
                 it++;
             }
         }

@@ -52,7 +52,7 @@ struct ldpc_b200_handle_s {
     int32_t* d_cptr = nullptr; int32_t* d_cedge = nullptr;
     int levels = 0, sms = 0;
     // row-parallel plan
-    int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0; size_t rp_smem = 0;
+    int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0; size_t rp_smem = 0;
     RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
     Slot slot[kSlots];
@@ -98,7 +98,7 @@ int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& w
     if (p->kernel < 0 || p->kernel > 3) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
     const bool generic = p->dtype != LDPC_DTYPE_I8 || p->schedule != LDPC_SCHED_LAYERED;
     if (generic && (p->kernel == 1 || p->kernel == 2)) { why = "kernels 1 and 2 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
-    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3)) { why = "generic engine: row degree > 64"; return LDPC_ERR_UNSUPPORTED; }
+    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
     if (p->dtype == LDPC_DTYPE_F32) {
         if (p->algo == LDPC_ALGO_OMS && (p->offset < 0 || p->llr_scale <= 0)) { why = "float OMS: offset >= 0 and llr_scale > 0 (offset is offset/llr_scale in channel units)"; return LDPC_ERR_INVALID; }
         if ((p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS) && !(p->factor1 > 0.0f && p->factor2 > 0.0f)) { why = "float NMS: factors must be positive"; return LDPC_ERR_INVALID; }
@@ -155,7 +155,7 @@ GpMode make_gp_mode(const ldpc_params_t& p)
 // Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table, (G, P) grouping.
 struct RpPlan {
     std::vector<RpStep> steps; std::vector<RpRun> runs; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of;
-    int G = 1, P = 1, m_elems = 0, pair_pad = 0, slots = 0;
+    int G = 1, P = 1, m_elems = 0, pair_pad = 0, slots = 0, static_nrows = 0;
 };
 
 int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
@@ -212,12 +212,17 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
             }
         plan.steps.push_back(st);
     }
+    // every way into an iteration ends with a group barrier (load, previous iteration, syndrome bookkeeping): the first level needs none
+    if (!plan.steps.empty()) plan.steps[0].sync = 0;
     // runs: consecutive steps that share one kernel instantiation (degree, stride, x86 quirk class)
     for (int i = 0; i < (int)plan.steps.size(); i++) {
         const RpStep& st = plan.steps[i];
         const int quirk = st.cls >= 1 ? 1 : 0;
-        if (!plan.runs.empty() && plan.runs.back().variant == (int)st.variant && plan.runs.back().quirk == quirk) plan.runs.back().count++;
-        else plan.runs.push_back(RpRun{ i, 1, (int)st.variant, quirk });
+        if (!plan.runs.empty() && plan.runs.back().variant == (int)st.variant && plan.runs.back().quirk == quirk && plan.runs.back().count < 32
+            && st.msg_off == plan.runs.back().msg_off0 + (uint32_t)plan.runs.back().count * st.stride * st.deg) {
+            plan.runs.back().syncmask |= (uint32_t)st.sync << plan.runs.back().count;
+            plan.runs.back().count++;
+        } else plan.runs.push_back(RpRun{ i, 1, (int)st.variant, quirk, st.msg_off, (uint32_t)st.sync, { 0u, 0u } });
     }
     // grouping: G warps share P pairs so that the P*nrows tasks of a step fill whole warps.  Score = lane efficiency x
     // occupancy (measured on 576x288, profiles/r01_sweep_groupings.jsonl: (3,4) with 18 warps 0.78 ms, (1,1) with 23 warps at
@@ -264,6 +269,10 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     if (h->prm.reserved[0] > 0 && h->prm.reserved[0] <= 4 && h->prm.reserved[1] > 0 && h->prm.reserved[1] <= 8) { plan.G = h->prm.reserved[0]; plan.P = h->prm.reserved[1]; }
     plan.pair_pad = pad_for(plan.P);
     plan.slots = slots_for(plan.G, plan.P, plan.pair_pad);
+    // static plan: uniform steps, every run specialised, at most one task per lane of a full group
+    bool all_special = true;
+    for (auto& r : plan.runs) all_special = all_special && r.variant != 0;
+    plan.static_nrows = (uniform && all_special && plan.P * nr0 <= 32 * plan.G && h->prm.reserved[3] == 0) ? nr0 : 0;
     return LDPC_OK;
 }
 
@@ -354,6 +363,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         a.idx_t = h->d_idx_t; a.edge_of = h->d_edge_of; a.steps = h->d_steps;
         a.runs = h->d_runs; a.nruns = h->rp_nruns; a.pair_words = h->rp_pair_words;
         a.frames = frames; a.n = c.n; a.m = c.m; a.nsteps = h->rp_nsteps; a.n_pad = h->rp_npad; a.m_elems = h->rp_melems;
+        a.static_nrows = h->rp_static;
         a.G = h->rp_G; a.P = h->rp_P; a.groups = h->rp_groups; a.slots = h->rp_slots; a.iters = iters;
         a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.prm = h->prm;
         const size_t pairs = (frames + 1) / 2;
@@ -493,7 +503,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         const int min_slots = params->kernel == 2 ? 1 : 8;
         if (slots >= min_slots) {
             h->kernel = 2; h->rp_G = plan.G; h->rp_P = plan.P; h->rp_slots = slots; h->rp_groups = (slots + plan.P - 1) / plan.P;
-            h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size();
+            h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size(); h->rp_static = plan.static_nrows;
             h->rp_smem = fixed_bytes(slots) + pair_bytes * slots;
             CREATE_TRY(cudaMalloc((void**)&h->d_runs, plan.runs.size() * sizeof(RpRun)));
             CREATE_TRY(cudaMemcpy(h->d_runs, plan.runs.data(), plan.runs.size() * sizeof(RpRun), cudaMemcpyHostToDevice));

@@ -11,7 +11,9 @@ def run(code_name, frames, iters, reps=12, rotate=6, **kw):
     dec = pkg.CGPUDecoder(code, nb_frames=frames, **kw)
     ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
     rotate = max(1, min(rotate, int(2e9 // (frames * code.n))))
-    d_llrs = [torch.empty((frames, code.n), dtype=torch.int8, device="cuda") for _ in range(rotate)]
+    tdt = {0: torch.int8, 1: torch.int16, 2: torch.float32}[dec.params.dtype]
+    rotate = max(1, min(rotate, int(2e9 // (frames * code.n * torch.empty((), dtype=tdt).element_size()))))
+    d_llrs = [torch.empty((frames, code.n), dtype=tdt, device="cuda") for _ in range(rotate)]
     d_hard = torch.empty((frames, code.n), dtype=torch.uint8, device="cuda")
     for b, d in enumerate(d_llrs):
         dec.awgn_device(d.data_ptr(), frames, pkg.sigma_for(2.0, code.k_info / code.n), 1, b * frames, ts.cuda_stream)
@@ -34,7 +36,14 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")        # e.g. "576x288:3:4" -> one run, for ncu
     ap.add_argument("--frames", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--runs", default="")        # JSON list of dicts: {"code":..., "frames":..., "iters":..., + CGPUDecoder keywords}
     a = ap.parse_args()
+    if a.runs:
+        for r in json.loads(a.runs):
+            r = dict(r)
+            if "group" in r: r["group"] = tuple(r["group"])
+            run(r.pop("code"), r.pop("frames", a.frames), r.pop("iters", 10), reps=r.pop("reps", a.reps), rotate=r.pop("rotate", 6), **r)
+        sys.exit(0)
     if a.only:
         name, G, P = a.only.split(":")
         run(name, a.frames, 10, reps=a.reps, rotate=1, group=(int(G), int(P)))
