@@ -20,6 +20,7 @@
 namespace ldpcb200 {
 
 #define RP_MAX_THREADS 768
+#define RP_STATIC_THREADS 576     // static plan: at most 18 warps per CTA -> 112 registers per thread
 #define RP_MAX_GROUPS 15          // named barriers 1..15
 
 struct RpStep {         // read by the kernel as one 128-bit load (first four words) — keep the field order
@@ -102,10 +103,11 @@ __device__ __forceinline__ void rp_row(uint32_t ub, uint32_t msa, uint32_t ixa, 
     RowState s;
     row_pass1<SEM, ALGO, Q, D>(xu, a, f, s, K);
     RowOut o; row_finish<SEM, ALGO>(s, D, K, msg_c, o);
+    RowOutS q; fold_sign(o, q);
 #pragma unroll
     for (int j = 0; j < D; j++) {
         h2 msg, unew;
-        pass2_edge_f(xu[j], a[j], f[j], o, K, msg, unew);
+        pass2_edge_s(xu[j], a[j], f[j], q, K, msg, unew);
         if (ET) {   // frozen frame (keep = 0xFFFF in its half) retains posterior and message
             unew = bits_h2((h2_bits(uo[j]) & keep) | (h2_bits(unew) & ~keep));
             if (!FIRST) msg = bits_h2((h2_bits(mo[j]) & keep) | (h2_bits(msg) & ~keep));
@@ -160,6 +162,7 @@ struct RpCtx {
 template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
 __device__ __forceinline__ void rp_run(const RpCtx& c, int first, int count, int valid_pairs, const RowConsts& K)
 {
+#pragma unroll 1
     for (int s = first; s < first + count; s++) {
         const uint4 sd = lds_u128(c.steps_s + 32u * s);         // {deg | nrows<<16, stride | cls<<16 | sync<<24, msg_off, magic}
         const int nrows = (int)(sd.x >> 16);
@@ -184,14 +187,69 @@ __device__ __forceinline__ void rp_run(const RpCtx& c, int first, int count, int
 // (profiles/r01_ncu_rp_v3_g34.txt: 32.9 warp instructions per warp-edge-update against ~22 in the row body.)
 struct RpLane { uint32_t ub, ms_lane, ix_lane, keep; bool active; };
 
+// row body with the addresses and the old messages already in registers (software-pipelined caller)
+template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void rp_row_pre(const uint32_t (&ua)[D], const h2 (&uo)[D], const h2 (&mo)[D], uint32_t msa, const RowConsts& K, h2 msg_c, uint32_t keep)
+{
+    uint32_t f[D];
+    h2 xu[D], a[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) xu[j] = FIRST ? uo[j] : __hmin2(__hadd2_sat(uo[j], __hneg2(mo[j])), K.top);
+    RowState s;
+    row_pass1<SEM, ALGO, Q, D>(xu, a, f, s, K);
+    RowOut o; row_finish<SEM, ALGO>(s, D, K, msg_c, o);
+    RowOutS q; fold_sign(o, q);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        h2 msg, unew;
+        pass2_edge_s(xu[j], a[j], f[j], q, K, msg, unew);
+        if (ET) {   // frozen frame (keep = 0xFFFF in its half) retains posterior and message
+            unew = bits_h2((h2_bits(uo[j]) & keep) | (h2_bits(unew) & ~keep));
+            if (!FIRST) msg = bits_h2((h2_bits(mo[j]) & keep) | (h2_bits(msg) & ~keep));
+        }
+        sts_u32(ua[j], h2_bits(unew));
+        sts_u32(msa + 4 * NR * j, h2_bits(msg));
+    }
+}
+
+// Software pipeline over the steps of a run: the index loads and the old messages of step s+1 belong to this lane alone
+// (no other lane writes them), so they are issued before step s's arithmetic and cross the level barrier in flight; only the
+// posterior gathers have to wait for the barrier.
 template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
 __device__ __forceinline__ void rp_run_static(const RpCtx& c, const RpRun& r, const RpLane& L, const RowConsts& K)
 {
     const h2 msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && FIRST && r.quirk) ? K.one : K.msg;
     uint32_t mask = r.syncmask, msa = L.ms_lane + 4u * r.msg_off0, ixa = L.ix_lane + 2u * r.msg_off0;
+    uint32_t ix[D];
+    h2 mo[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) { ix[j] = 0u; mo[j] = bits_h2(0u); }
+    if (L.active) {
+#pragma unroll
+        for (int j = 0; j < D; j++) ix[j] = lds_u16(ixa + 2 * NR * j);
+        if (!FIRST) {
+#pragma unroll
+            for (int j = 0; j < D; j++) mo[j] = bits_h2(lds_u32(msa + 4 * NR * j));
+        }
+    }
+#pragma unroll 1
     for (int s = 0; s < r.count; s++, mask >>= 1, msa += 4u * NR * D, ixa += 2u * NR * D) {
         if (mask & 1u) group_sync(c.G, c.bar);
-        if (L.active) rp_row<SEM, ALGO, D, NR, FIRST, ET, Q>(L.ub, msa, ixa, K, msg_c, L.keep);
+        if (L.active) {
+            uint32_t ua[D];
+            h2 uo[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) { ua[j] = L.ub + ix[j]; uo[j] = bits_h2(lds_u32(ua[j])); }
+            rp_row_pre<SEM, ALGO, D, NR, FIRST, ET, Q>(ua, uo, mo, msa, K, msg_c, L.keep);
+            if (s + 1 < r.count) {      // the row's registers are dead here: the next step's loads cross the barrier in flight
+#pragma unroll
+                for (int j = 0; j < D; j++) ix[j] = lds_u16(ixa + 2 * NR * (D + j));
+                if (!FIRST) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) mo[j] = bits_h2(lds_u32(msa + 4 * NR * (D + j)));
+                }
+            }
+        }
     }
 }
 
@@ -347,8 +405,10 @@ __device__ __forceinline__ void rp_store_pair(const RpArgs& A, size_t f0, const 
     }
 }
 
-template <int SEM, int ALGO, bool ET>
-__global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __grid_constant__ RpArgs A)
+// STAT = static plan (see rp_run_static): its own instantiation so that it gets the register budget of an 18-warp CTA
+// (the software pipeline keeps two steps of addresses and messages live) and carries none of the descriptor-driven code.
+template <int SEM, int ALGO, bool ET, bool STAT>
+__global__ void __launch_bounds__(STAT ? RP_STATIC_THREADS : RP_MAX_THREADS, 1) rp_decode_kernel(const __grid_constant__ RpArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: steps | runs | idx | flags (2 words per pair slot) | pair states
@@ -406,7 +466,7 @@ __global__ void __launch_bounds__(RP_MAX_THREADS, 1) rp_decode_kernel(const __gr
         }
         group_sync(c.G, c.bar);
         RpLane L;                                          // static plan: this lane's (pair, row slot) for the whole decode
-        const bool stat = A.static_nrows > 0;
+        const bool stat = STAT;
         {
             const uint32_t lp = stat ? (uint32_t)c.gl / (uint32_t)A.static_nrows : 0u, lz = (uint32_t)c.gl - lp * (uint32_t)A.static_nrows;
             L.active = stat && (int)lp < valid;

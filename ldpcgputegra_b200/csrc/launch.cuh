@@ -31,9 +31,15 @@ template <int SEM, int ALGO, bool ET>
 static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStream_t st)
 {
     // per-device attribute, cheap and idempotent: set on every launch so any device of the process is covered
-    cudaError_t e = cudaFuncSetAttribute(rp_decode_kernel<SEM, ALGO, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    rp_decode_kernel<SEM, ALGO, ET><<<blocks, threads, smem, st>>>(a);
+    if (a.static_nrows > 0) {
+        cudaError_t e = cudaFuncSetAttribute(rp_decode_kernel<SEM, ALGO, ET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        rp_decode_kernel<SEM, ALGO, ET, true><<<blocks, threads, smem, st>>>(a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(rp_decode_kernel<SEM, ALGO, ET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        rp_decode_kernel<SEM, ALGO, ET, false><<<blocks, threads, smem, st>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 #define LDPC_CASE(FN, SEM, ALGO, ...) return et ? FN<SEM, ALGO, true>(__VA_ARGS__) : FN<SEM, ALGO, false>(__VA_ARGS__)

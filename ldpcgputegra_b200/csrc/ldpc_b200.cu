@@ -273,6 +273,11 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     bool all_special = true;
     for (auto& r : plan.runs) all_special = all_special && r.variant != 0;
     plan.static_nrows = (uniform && all_special && plan.P * nr0 <= 32 * plan.G && h->prm.reserved[3] == 0) ? nr0 : 0;
+    if (plan.static_nrows) {   // the static kernel is compiled for at most RP_STATIC_THREADS threads
+        const int max_groups = RP_STATIC_THREADS / (32 * plan.G);
+        if (max_groups < 1) plan.static_nrows = 0;
+        else plan.slots = std::min(plan.slots, max_groups * plan.P);
+    }
     return LDPC_OK;
 }
 
@@ -500,7 +505,11 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         const size_t pair_bytes = (size_t)h->rp_pair_words * 4;
         auto fixed_bytes = [&](int slots_) { return plan.steps.size() * sizeof(RpStep) + plan.runs.size() * sizeof(RpRun) + (((size_t)plan.m_elems * 2 + 15) / 16) * 16 + (((size_t)slots_ * 8 + 15) / 16) * 16; };
         const int slots = plan.slots;
-        const int min_slots = params->kernel == 2 ? 1 : 8;
+        // measured (profiles/r01_sweep_v5.jsonl): with >= 4 pairs per SM the on-chip kernel wins at every batch size (2304x1152,
+        // 5 pairs: 14.0 M frames/s against 4.2 for the frame-parallel kernel at 64 Ki frames); with 2-3 pairs (4000x2000) it wins
+        // for small batches (2.3 vs 0.6 M frames/s at 16 Ki) but the frame-parallel kernel overtakes it once the batch fills the
+        // GPU with threads (4.0 M frames/s at 128 Ki)
+        const int min_slots = params->kernel == 2 ? 1 : (h->max_frames >= 98304 ? 4 : 2);
         if (slots >= min_slots) {
             h->kernel = 2; h->rp_G = plan.G; h->rp_P = plan.P; h->rp_slots = slots; h->rp_groups = (slots + plan.P - 1) / plan.P;
             h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size(); h->rp_static = plan.static_nrows;

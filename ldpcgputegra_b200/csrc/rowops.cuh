@@ -192,6 +192,23 @@ __device__ __forceinline__ void pass2_edge_f(h2 xu, h2 a, uint32_t f, const RowO
     unew = __hmin2(__hfma2_sat(sigma, mag, xu), K.top);
 }
 
+// The same with the row's sign folded into the two magnitudes once per row (sc1 = +-c1, sdc = +-(c2 - c1)): the edge's own
+// sign is then a single LOP3 on the bit pattern, (f & 0x8000) ^ mag — 5 instructions per edge instead of 6, one FMA-pipe op
+// fewer.  A zero magnitude may come out as -0: it adds and compares like +0, and no flag is ever taken from a message.
+struct RowOutS { h2 sc1, sdc, nmin1; };
+__device__ __forceinline__ void fold_sign(const RowOut& o, RowOutS& q)
+{
+    const h2 rs = bits_h2(o.sgn);             // +-1.0 per half: row parity ^ degree parity
+    q.sc1 = __hmul2(rs, o.c1); q.sdc = __hmul2(rs, o.dc); q.nmin1 = o.nmin1;
+}
+__device__ __forceinline__ void pass2_edge_s(h2 xu, h2 a, uint32_t f, const RowOutS& q, const RowConsts& K, h2& msg, h2& unew)
+{
+    const h2 d = __hfma2_sat(a, K.k256, q.nmin1);
+    const h2 smag = __hfma2(d, q.sdc, q.sc1);
+    msg = bits_h2(and_xor(f, 0x80008000u, h2_bits(smag)));
+    unew = __hmin2(__hadd2_sat(xu, msg), K.top);
+}
+
 // pass 2, one edge: returns the new message (signed, /256) and the new biased posterior
 template <int SEM>
 __device__ __forceinline__ void pass2_edge(h2 xu, h2 a, const RowOut& o, const RowConsts& K, h2& msg, h2& unew)
