@@ -44,6 +44,21 @@ def peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the decode kernel, from the newest committed `ncu --set full`
+    summary of this workload (profiles/rNN_ncu_rp_v*.json, written by tools/ncu_summary.py).  None when no capture is committed."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*_ncu_rp_v*.json")):
+        try:
+            l0 = json.loads(f.read_text())["launches"][0]
+            tot = sum(float(l0[k]["value"]) * unit[l0[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            best = (tot, f.name)
+        except Exception:
+            continue
+    return best
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line), via NVML."""
 
@@ -254,6 +269,7 @@ def main():
     host_fe = int(h_hard.array[:, :k_info].any(axis=1).sum())
 
     hbm_peak, sm_max_mhz, peak_src = peaks()
+    traffic = ncu_traffic() if F == FRAMES else None
     bytes_per_frame = n + n                      # int8 LLR in + one byte per bit out (the reference's output format)
     per_gpu_fps = fps / world
     achieved_gbs = per_gpu_fps * bytes_per_frame / 1e9
@@ -262,7 +278,9 @@ def main():
     line = {"metric": "decoded info throughput at 10 iterations", "value": fps * k_info / 1e9, "unit": "Gb/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
             "config": config,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+                         "algorithmic_bytes_per_launch": F * bytes_per_frame,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_per_frame,
                          "note": "on-chip state: HBM sees LLR-in + bits-out only, so this fraction is small by construction; the binding roof is sm_roofline"},
             "sm_roofline": {"bound": "sm_int_issue", "achieved": sm_ops / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s", "frac": sm_ops / int_peak,
@@ -270,7 +288,7 @@ def main():
                             "note": "canonical scalar-int cost of SURVEY 8d; two frames per instruction (f16x2) may exceed 1.0"},
             "e2e": {"value": e2e_fps * k_info / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": F * n, "d2h_bytes_per_step": F * n,
                     "frames_per_s": e2e_fps, "api": "ldpc_b200_decode (blocking, pinned host buffers, 4 stream slots)"},
-            "gpu_launches": int(launches), "kernel": {1: "frame-parallel (HBM state)", 2: "row-parallel on-chip"}[kernel],
+            "gpu_launches": int(launches), "kernel": {1: "frame-parallel (HBM state)", 2: "row-parallel on-chip", 3: "generic engine", 4: "frame-parallel, bulk-copy staged"}[kernel],
             "clocks": clocks, "frames_per_s": fps, "air_gbps": fps * n / 1e9,
             "ber_fer": {"frames": F, "bit_errors": be, "frame_errors": fe, "fer": fe / F, "e2e_frame_errors_last_batch": host_fe}}
 

@@ -197,6 +197,9 @@ def default_params(**kw) -> ParamsT:
         if k == "chunk_waves":    # waves per pipeline chunk of decode() (experiment knob)
             p.reserved[2] = v
             continue
+        if k == "fs_stages":      # ring depth of the staged frame-parallel kernel (A/B experiments)
+            p.reserved[4] = int(v)
+            continue
         if k == "no_static":      # force the descriptor-driven step loop of the on-chip kernel (A/B experiments)
             p.reserved[3] = int(v)
             continue

@@ -32,52 +32,63 @@ struct FpArgs {
 
 #define FP_BLOCK 128
 
-// ---- one row, degree known at compile time, x kept in registers --------------------------------------------------
+// ---- the arithmetic of one row on packed words: wv[j] = biased posteriors of 4 frames, wm[j] = messages + 128 -----------
 template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
-__device__ __forceinline__ void fp_row(const FpArgs& A, int t, size_t e, const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi)
+__device__ __forceinline__ void fp_row_math(const uint32_t (&wv)[D], const uint32_t (&wm)[D], const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi,
+                                            uint32_t (&nv)[D], uint32_t (&nm)[D])
 {
-    uint32_t idx[D], wv[D], wm[D];
-#pragma unroll
-    for (int j = 0; j < D; j++) idx[j] = __ldg(A.pos + e + j);
-#pragma unroll
-    for (int j = 0; j < D; j++) wv[j] = A.V[(size_t)idx[j] * A.T + t];
-    if (!FIRST) {
-#pragma unroll
-        for (int j = 0; j < D; j++) wm[j] = A.MSG[(e + j) * A.T + t];
-    }
     uint32_t ov[2][D], om[2][D];
     const h2 inv256 = h2_const(1.0f / 256.0f), half = h2_const(0.5f), m4 = h2_const(-4.0f);
 #pragma unroll
     for (int g = 0; g < 2; g++) {
-        RowState s; row_begin(s, K);
         h2 xu[D], a[D];
+        uint32_t f[D];
 #pragma unroll
         for (int j = 0; j < D; j++) {
             h2 wU = g ? bytes23_to_w(wv[j]) : bytes01_to_w(wv[j]);
             h2 nM = m4;                                                        // -(0) - 4
             if (!FIRST) { h2 wM = g ? bytes23_to_w(wm[j]) : bytes01_to_w(wm[j]); nM = __hfma2(wM, __hneg2(inv256), half); }
             xu[j] = __hmin2(__hfma2_sat(wU, inv256, nM), K.top);               // clamp(v - m) in the biased domain
-            a[j] = pass1_edge<SEM, ALGO, Q>(s, xu[j], K);
         }
+        RowState s;
+        row_pass1<SEM, ALGO, Q, D>(xu, a, f, s, K);                            // pairwise (min1, min2) merge, 3-input parity xors
         RowOut o; row_finish<SEM, ALGO>(s, D, K, K.msg_c, o);
+        RowOutS q; fold_sign(o, q);
 #pragma unroll
         for (int j = 0; j < D; j++) {
             h2 msg, unew;
-            pass2_edge<SEM>(xu[j], a[j], o, K, msg, unew);
+            pass2_edge_s(xu[j], a[j], f[j], q, K, msg, unew);
             ov[g][j] = q_to_w(unew, 0.0f);
             om[g][j] = q_to_w(msg, 128.0f);
         }
     }
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        uint32_t nv = pack_bytes(ov[0][j], ov[1][j]), nm = pack_bytes(om[0][j], om[1][j]);
+        nv[j] = pack_bytes(ov[0][j], ov[1][j]); nm[j] = pack_bytes(om[0][j], om[1][j]);
         if (ET) {   // frozen frames keep their state
             const uint32_t keep = __byte_perm(keep_lo, keep_hi, 0x6420);
-            nv = (wv[j] & keep) | (nv & ~keep);
-            nm = FIRST ? nm : ((wm[j] & keep) | (nm & ~keep));
+            nv[j] = (wv[j] & keep) | (nv[j] & ~keep);
+            nm[j] = FIRST ? nm[j] : ((wm[j] & keep) | (nm[j] & ~keep));
         }
-        A.V[(size_t)idx[j] * A.T + t] = nv;
-        A.MSG[(e + j) * A.T + t] = nm;
+    }
+}
+
+// ---- one row, degree known at compile time, x kept in registers --------------------------------------------------
+template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void fp_row(const FpArgs& A, int t, size_t e, const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi)
+{
+    uint32_t idx[D], wv[D], wm[D], nv[D], nm[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) idx[j] = __ldg(A.pos + e + j);
+#pragma unroll
+    for (int j = 0; j < D; j++) wv[j] = A.V[(size_t)idx[j] * A.T + t];
+#pragma unroll
+    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : A.MSG[(e + j) * A.T + t];
+    fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        A.V[(size_t)idx[j] * A.T + t] = nv[j];
+        A.MSG[(e + j) * A.T + t] = nm[j];
     }
 }
 

@@ -1,0 +1,174 @@
+// kernel_fs.cuh — frame-parallel decoder with the HBM-resident state STAGED through shared memory by the bulk-copy engine.
+//
+// Same mapping and arithmetic as kernel_fp.cuh (one thread = 4 frames, rows strictly in reference order: the only legal
+// mapping for DVB-S2 64800x32400, whose reference order is a 32 399-deep chain — SURVEY App. C), but the loads no longer sit
+// on the threads' critical path: a producer warp walks the row list K rows ahead of the consumers and pulls every row's
+// posterior lines V[idx][t0..t0+127] and message lines MSG[e][t0..t0+127] (512 contiguous bytes each) into a K-stage ring with
+// cp.async.bulk (TMA, non-tensor form) completing on an mbarrier per stage; consumers read their word from the stage, do the
+// row, store the results straight to HBM, and hand the stage back.  Memory-level parallelism is then K rows x 14 lines x 512 B
+// per CTA whatever the number of resident threads — the frame-parallel kernel needs ~60 K resident threads (256 Ki frames) to
+// pull 55 % of HBM bandwidth, this one is meant to get there with a 64 Ki-frame batch.
+// (The reference re-reads both arrays through a per-row __syncthreads pair: code/gpu_fixed/decoder_oms/cuda/CUDA_OMS_SIMD.cu:141-187.)
+//
+// Staleness.  A line prefetched for row q was read up to K rows early, so it is wrong if one of the K rows before q wrote the
+// same variable.  The host marks those edges (bit 31 of pos2[e], window FS_HAZARD rows, cyclic over the iteration boundary);
+// the producer skips them and the consumer loads that word itself, after its own stores in program order (a V word is only ever
+// written by its own thread).  DVB-S2: exactly the staircase parity bit of each row.  Everything else is ordered by
+// st.global -> fence.proxy.async -> mbarrier arrive (empty) -> producer wait -> cp.async.bulk.
+// A store followed one row later by a load of the same word would still cost an L2 round trip per row (first measurement:
+// 910 ns per DVB-S2 row, all of it this load), so the last FS_FWD rows' outputs are also kept in a small per-thread ring in
+// shared memory and flagged edges whose writer is that close read the ring instead (pos2 bits 30..26: forward, rows back - 1,
+// edge slot of the writer).  Messages are private to their edge and a whole iteration old when they are fetched.
+// Roofline: HBM, 4*M bytes per frame-iteration as for kernel_fp.
+#pragma once
+#include "kernel_fp.cuh"
+
+namespace ldpcb200 {
+
+#define FS_CONSUMERS 128                 // consumer threads per CTA (4 warps); +1 producer warp
+#define FS_THREADS (FS_CONSUMERS + 32)
+#define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line
+#define FS_MAXDEG 8
+#define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
+#define FS_FWD 4                         // rows whose outputs stay in the forwarding ring
+#define FS_F_HAZARD 0x80000000u          // pos2 flags: not prefetched (written within the hazard window) ...
+#define FS_F_FWD    0x40000000u          // ... and the writer is at most FS_FWD rows back: bits 29..28 = rows back - 1, bits 27..25 = its edge slot
+#define FS_IDX_MASK 0x01FFFFFFu
+
+struct FsArgs {
+    uint32_t* V;
+    uint32_t* MSG;
+    const uint32_t* pos2;    // [m] variable index | hazard << 31
+    int T, n, m, nb_deg;
+    int deg[LDPC_MAX_DEG_CLASSES];
+    int rows[LDPC_MAX_DEG_CLASSES];
+    int iters, stages, max_deg;
+    ldpc_params_t prm;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// generic-proxy global writes -> visible to later async-proxy (bulk copy) reads.  The .global form is a bare FENCE.VIEW.ASYNC.G;
+// the unqualified form costs a MEMBAR.ALL.GPU on top (cuobjdump)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// one row for the consumer: words come from the stage unless the edge is flagged (hazard) — then from global, after this
+// thread's own earlier stores
+// The stage of the PREVIOUS row is handed back here, between this row's arithmetic and its stores: the fence then only has
+// to cover stores that were issued a whole row ago, so it never waits on fresh ones.
+template <int SEM, int ALGO, int D, bool FIRST, bool Q>
+__device__ __forceinline__ void fs_row(const FsArgs& A, int t, int tid, size_t e, uint32_t stage_s, const RowConsts& K, uint32_t prev_empty, int lane,
+                                       uint32_t fwd_s, uint32_t q, bool fwd_ok)
+{
+    uint32_t p2[D], wv[D], wm[D], nv[D], nm[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (p2[j] & FS_F_HAZARD) {
+            if ((p2[j] & FS_F_FWD) && fwd_ok) {
+                const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 25) & 7u;
+                wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * FS_CONSUMERS + tid) * 4u);
+            } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
+        } else wv[j] = lds_u32(stage_s + j * FS_LINE + 4 * tid);
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * FS_LINE + 4 * tid);
+    fp_row_math<SEM, ALGO, D, FIRST, false, Q>(wv, wm, K, 0u, 0u, nv, nm);
+    fence_proxy_async_global();                    // the previous rows' stores, before any later bulk copy of the same lines
+    __syncwarp();
+    if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t] = nv[j];
+        A.MSG[(e + j) * A.T + t] = nm[j];
+        sts_u32(fwd_s + (((q & (FS_FWD - 1)) * FS_MAXDEG + j) * FS_CONSUMERS + tid) * 4u, nv[j]);
+    }
+}
+
+template <int SEM, int ALGO>
+__global__ void __launch_bounds__(FS_THREADS) fs_decode_kernel(const __grid_constant__ FsArgs A)
+{
+    extern __shared__ __align__(128) unsigned char fs_smem[];
+    // layout: full[K] | empty[K] | pad to 128 | forwarding ring | K stages of 2*max_deg lines
+    const int Kst = A.stages;
+    const uint32_t bars = smem_u32(fs_smem);
+    const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
+    const uint32_t ring = fwd_s + FS_FWD * FS_MAXDEG * FS_LINE;
+    const uint32_t stage_bytes = (uint32_t)(2 * A.max_deg) * FS_LINE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * FS_CONSUMERS;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < Kst; k++) { mbar_init(bars + 8 * k, 1); mbar_init(bars + 8 * (Kst + k), FS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FS_CONSUMERS / 32) {
+        // ---------------- producer warp: lanes 0-7 fetch the posterior lines, lanes 8-15 the message lines of one row ----------
+        int stage = 0; uint32_t phase = 0;
+        const int j = lane & 7;
+        for (int it = 0; it < A.iters; it++) {
+            size_t e = 0;
+            for (int c = 0; c < A.nb_deg; c++) {
+                const int D = A.deg[c];
+                for (int r = 0; r < A.rows[c]; r++, e += D) {
+                    if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
+                    __syncwarp();
+                    const uint32_t p2 = (lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : 0x80000000u;
+                    const bool do_v = lane < 8 && j < D && !(p2 & FS_F_HAZARD);
+                    const bool do_m = lane >= 8 && lane < 16 && j < D && it > 0;
+                    const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, do_v || do_m));
+                    const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
+                    if (lane == 0) mbar_arrive_expect_tx(full, n_lines * FS_LINE);
+                    __syncwarp();
+                    if (do_v) bulk_g2s(dst0 + j * FS_LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), FS_LINE, full);
+                    if (do_m) bulk_g2s(dst0 + (A.max_deg + j) * FS_LINE, A.MSG + ((e + j) * A.T + t0), FS_LINE, full);
+                    if (++stage == Kst) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ---------------------------------------------------------------------------------------------
+    const int tid = threadIdx.x, t = t0 + tid;
+    RowConsts K; make_consts<SEM>(K, A.prm);
+    int stage = 0; uint32_t phase = 0, prev_empty = 0u, q = 0u;
+    for (int it = 0; it < A.iters; it++) {
+        size_t e = 0;
+        for (int c = 0; c < A.nb_deg; c++) {
+            const int D = A.deg[c];
+            const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
+            // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
+            K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
+            for (int r = 0; r < A.rows[c]; r++, e += D) {
+                mbar_wait(bars + 8 * stage, phase);
+                const bool fwd_ok = q >= FS_FWD;            // the first rows of the first iteration have no predecessors in the ring
+                const uint32_t st_s = ring + (uint32_t)stage * stage_bytes;
+#define FS_CASE(DD)                                                                                                   \
+    case DD:                                                                                                          \
+        if (it == 0) { if (quirk) fs_row<SEM, ALGO, DD, true, true>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, true, false>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
+        else         { if (quirk) fs_row<SEM, ALGO, DD, false, true>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, false, false>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
+        break;
+                switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) }
+#undef FS_CASE
+                prev_empty = bars + 8 * (Kst + stage); q++;
+                if (++stage == Kst) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
+}  // namespace ldpcb200

@@ -74,15 +74,6 @@ __device__ __forceinline__ void group_sync(int G, int bar_id)
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(G * 32) : "memory");
 }
 
-// Shared memory is addressed through 32-bit shared-window offsets and explicit ld/st.shared in the hot loop: generic 64-bit
-// pointers cost 3-4 extra integer instructions per access (first profile: profiles/r01_ncu_rp_v2_g11.txt, 36.7 warp
-// instructions per edge against 21 in the row body itself).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
 // ---- one row, degree and stride known at compile time: every per-edge address is base + immediate --------------------
 // ub = shared address of the pair's U, msa = shared address of MS[msg_off + z], ixa = shared address of idx[msg_off + z]
 template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>

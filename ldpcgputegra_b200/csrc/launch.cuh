@@ -4,17 +4,23 @@
 #include <cuda_runtime.h>
 #include "kernel_fp.cuh"
 #include "kernel_rp.cuh"
+#include "kernel_fs.cuh"
 
 namespace ldpcb200 {
 
 // algo: ldpc_algo_t (2NMS shares the NMS instantiation: only the rescale constants differ). Returns cudaError_t as int.
 typedef int (*fp_launch_fn)(int algo, int et, const FpArgs& args, int blocks, cudaStream_t st);
+typedef int (*fs_launch_fn)(int algo, const FsArgs& args, int blocks, size_t smem, cudaStream_t st);
 typedef int (*rp_launch_fn)(int algo, int et, const RpArgs& args, int blocks, int threads, size_t smem, cudaStream_t st);
 
 int launch_fp_x86(int, int, const FpArgs&, int, cudaStream_t);
 int launch_fp_uniform(int, int, const FpArgs&, int, cudaStream_t);
 int launch_fp_arm(int, int, const FpArgs&, int, cudaStream_t);
 int launch_fp_gpu(int, int, const FpArgs&, int, cudaStream_t);
+int launch_fs_x86(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fs_uniform(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fs_arm(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fs_gpu(int, const FsArgs&, int, size_t, cudaStream_t);
 int launch_rp_x86(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
 int launch_rp_uniform(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
 int launch_rp_arm(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
@@ -40,6 +46,14 @@ static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStre
         if (e != cudaSuccess) return (int)e;
         rp_decode_kernel<SEM, ALGO, ET, false><<<blocks, threads, smem, st>>>(a);
     }
+    return (int)cudaGetLastError();
+}
+template <int SEM, int ALGO>
+static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fs_decode_kernel<SEM, ALGO><<<blocks, FS_THREADS, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 #define LDPC_CASE(FN, SEM, ALGO, ...) return et ? FN<SEM, ALGO, true>(__VA_ARGS__) : FN<SEM, ALGO, false>(__VA_ARGS__)

@@ -55,6 +55,7 @@ struct ldpc_b200_handle_s {
     int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0; size_t rp_smem = 0;
     RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
+    uint32_t* d_pos2 = nullptr; int fs_max_deg = 0;    // staged frame-parallel kernel: edge table with hazard flags
     Slot slot[kSlots];
     bool debug = false;
     int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_post_bytes = 0, dbg_msgs_bytes = 0, dbg_frames = 0; int dbg_iters = 0;
@@ -95,9 +96,9 @@ int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& w
     if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
     if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
     if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
-    if (p->kernel < 0 || p->kernel > 3) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
+    if (p->kernel < 0 || p->kernel > 4) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
     const bool generic = p->dtype != LDPC_DTYPE_I8 || p->schedule != LDPC_SCHED_LAYERED;
-    if (generic && (p->kernel == 1 || p->kernel == 2)) { why = "kernels 1 and 2 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
+    if (generic && (p->kernel == 1 || p->kernel == 2 || p->kernel == 4)) { why = "kernels 1, 2 and 4 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
     for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
     if (p->dtype == LDPC_DTYPE_F32) {
         if (p->algo == LDPC_ALGO_OMS && (p->offset < 0 || p->llr_scale <= 0)) { why = "float OMS: offset >= 0 and llr_scale > 0 (offset is offset/llr_scale in channel units)"; return LDPC_ERR_INVALID; }
@@ -289,7 +290,7 @@ void destroy_impl(ldpc_handle h)
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
-    cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos);
+    cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2);
     cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge);
     free(h->code.pos);
     delete h;
@@ -380,7 +381,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         return LDPC_OK;
     }
     // frame-parallel: interleave -> decode -> de-interleave + hard decision
-    const int T = (int)(((frames + 3) / 4 + 31) / 32 * 32);
+    const int tq = h->kernel == 4 ? FS_CONSUMERS : 32;
+    const int T = (int)(((frames + 3) / 4 + tq - 1) / tq * tq);
     int rc;
     if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
     if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
@@ -397,9 +399,28 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (size_t)4 * T))) return rc;
         d_it4 = s.d_iters; a.iters_done = d_it4;
     }
+    if (h->kernel == 4) {
+        FsArgs f{};
+        f.V = s.d_V; f.MSG = s.d_MSG; f.pos2 = h->d_pos2; f.T = T; f.n = c.n; f.m = c.m; f.nb_deg = c.nb_deg;
+        for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { f.deg[i] = c.deg[i]; f.rows[i] = c.rows[i]; }
+        f.iters = iters; f.max_deg = h->fs_max_deg; f.prm = h->prm;
+        // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
+        const int ctas = T / FS_CONSUMERS, per_sm = std::min(4, (ctas + h->sms - 1) / h->sms);
+        const size_t stage_bytes = (size_t)2 * f.max_deg * FS_LINE;
+        int stages = (int)(((size_t)(220 * 1024) / per_sm - (size_t)FS_FWD * FS_MAXDEG * FS_LINE - 256) / stage_bytes);
+        stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
+        if (h->prm.reserved[4] >= 2 && h->prm.reserved[4] < FS_HAZARD) stages = h->prm.reserved[4];     // experiment knob
+        f.stages = stages;
+        const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + (size_t)FS_FWD * FS_MAXDEG * FS_LINE + stages * stage_bytes;
+        fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fs_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fs_uniform
+                        : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fs_arm : launch_fs_gpu;
+        if (iters > 0) CU_TRY(h, (cudaError_t)fn(h->prm.algo, f, ctas, smem, st));
+        if (d_it4) CU_TRY(h, cudaMemsetAsync(d_it4, iters, (size_t)4 * T, st));          // no early termination in this kernel: every frame runs `iters`
+    } else {
     fp_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fp_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fp_uniform
                     : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fp_arm : launch_fp_gpu;
     CU_TRY(h, (cudaError_t)fn(h->prm.algo, et, a, (T + FP_BLOCK - 1) / FP_BLOCK, st));
+    }
     if (h->prm.out_format == LDPC_OUT_PACKED) deinterleave_hard_kernel<true><<<tg, 256, 0, st>>>(s.d_V, d_hard, frames, c.n, T, lo);
     else deinterleave_hard_kernel<false><<<tg, 256, 0, st>>>(s.d_V, d_hard, frames, c.n, T, lo);
     CU_TRY(h, cudaGetLastError());
@@ -496,7 +517,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         CREATE_TRY(cudaMalloc((void**)&h->d_cedge, cedge.size() * sizeof(int32_t)));
         CREATE_TRY(cudaMemcpy(h->d_cedge, cedge.data(), cedge.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
-    if (!generic && code->n <= 16383 && params->kernel != 1) {
+    if (!generic && code->n <= 16383 && params->kernel != 1 && params->kernel != 4) {
         RpPlan plan;
         if ((rc = build_rp_plan(h, plan, (size_t)prop.sharedMemPerBlockOptin))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
         h->rp_npad = (code->n + 3) / 4 * 4;
@@ -524,6 +545,39 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMemcpy(h->d_edge_of, plan.edge_of.data(), plan.edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the row-parallel kernel"); }
     } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 16383"); }
+    // frame-parallel family: the staged variant (kernel 4) when the code allows it — no early termination (its producer runs a
+    // fixed row list), degrees 3..8, enough rows for the hazard window to be a small part of an iteration
+    if (h->kernel == 1) {
+        bool ok = params->early_term == LDPC_ET_NONE && code->n_checks >= 8 * FS_HAZARD;
+        int dmax = 0;
+        for (int i = 0; i < code->nb_deg; i++) { ok = ok && code->deg[i] >= 3 && code->deg[i] <= FS_MAXDEG && code->n <= (int)FS_IDX_MASK; dmax = std::max(dmax, code->deg[i]); }
+        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs early_term off, row degrees 3..8 and >= 128 rows"); }
+        if (ok && params->kernel != 1) {
+            // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
+            std::vector<uint32_t> pos2((size_t)code->m);
+            std::vector<long> last((size_t)code->n, -(long)(1 << 30));
+            std::vector<int> last_slot((size_t)code->n, 0);
+            for (int lap = 0; lap < 2; lap++) {
+                long q = (long)lap * code->n_checks; size_t e = 0;
+                for (int k = 0; k < code->nb_deg; k++)
+                    for (int r = 0; r < code->rows[k]; r++, q++)
+                        for (int j = 0; j < code->deg[k]; j++, e++) {
+                            const uint32_t v = code->pos[e];
+                            const long back = q - last[v];
+                            if (lap == 1) {
+                                uint32_t w = v;
+                                if (back <= FS_HAZARD) w |= FS_F_HAZARD;
+                                if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << 25);
+                                pos2[e] = w;
+                            }
+                            last[v] = q; last_slot[v] = j;
+                        }
+            }
+            CREATE_TRY(cudaMalloc((void**)&h->d_pos2, pos2.size() * sizeof(uint32_t)));
+            CREATE_TRY(cudaMemcpy(h->d_pos2, pos2.data(), pos2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            h->kernel = 4; h->fs_max_deg = dmax;
+        }
+    }
     if (h->kernel != 2 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);
 #undef CREATE_TRY
     // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
@@ -546,8 +600,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     switch (what) {
     case LDPC_INFO_KERNEL: *value = h->kernel; break;
     case LDPC_INFO_LEVELS: *value = h->levels; break;
-    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : (h->kernel == 3 ? 0 : 16384); break;
-    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : FP_BLOCK * 4); break;
+    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : (h->kernel == 1 ? 16384 : 0); break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : (h->kernel == 4 ? FS_CONSUMERS * 4 : FP_BLOCK * 4)); break;
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;
@@ -591,7 +645,7 @@ int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* ha
     if (iters_done) {
         if (h->kernel == 2) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
         else if (h->kernel == 3) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (frames + 31) / 32 * 32))) return rc; d_it = s.d_iters; }
-        else { const size_t T = ((frames + 3) / 4 + 31) / 32 * 32; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
+        else { const size_t tq = h->kernel == 4 ? FS_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
     }
     CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n * el, cudaMemcpyHostToDevice, s.stream));
     const bool dbg = h->debug && slot == 0;
