@@ -167,6 +167,10 @@ int  ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* h
 int  ldpc_b200_sync(ldpc_handle h, int slot /* -1 = all */);
 int  ldpc_b200_host_alloc(void** p, size_t bytes);              /* pinned; ref: CUDA_MALLOC_HOST custom_cuda.cu:30-60, CTrame.cpp:38-41 */
 int  ldpc_b200_host_free(void* p);
+/* device buffers for the device-resident entry points below, for C hosts that do not link the CUDA runtime themselves
+ * (ref: CUDA_MALLOC_DEVICE code/gpu_fixed/custom_api/custom_cuda.cu:62-142).  Allocated on the handle's device. */
+int  ldpc_b200_device_alloc(ldpc_handle h, void** p, size_t bytes);
+int  ldpc_b200_device_free(ldpc_handle h, void* p);
 
 /* decode with DEVICE buffers on a caller-supplied CUDA stream (cudaStream_t passed as void*; NULL = handle's slot-0 stream).
  * This is what `value` in bench.py times.  d_iters_done nullable. */

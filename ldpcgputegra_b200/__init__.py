@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
         "ldpc_b200_sync": (i32, [vp, i32]),
         "ldpc_b200_host_alloc": (i32, [C.POINTER(vp), sz]),
         "ldpc_b200_host_free": (i32, [vp]),
+        "ldpc_b200_device_alloc": (i32, [vp, C.POINTER(vp), sz]),
+        "ldpc_b200_device_free": (i32, [vp, vp]),
         "ldpc_b200_decode_device": (i32, [vp, vp, vp, sz, i32, vp, vp]),
         "ldpc_b200_set_debug": (i32, [vp, i32]),
         "ldpc_b200_debug_state": (i32, [vp, vp, vp, sz]),
@@ -113,7 +115,7 @@ EXPORTS = ["ldpc_b200_abi_version", "ldpc_b200_device_count", "ldpc_b200_status_
            "ldpc_b200_load_code_header", "ldpc_b200_load_code_table", "ldpc_b200_save_code_table", "ldpc_b200_check_code",
            "ldpc_b200_free_code", "ldpc_b200_level_schedule", "ldpc_b200_create", "ldpc_b200_destroy", "ldpc_b200_last_error",
            "ldpc_b200_get_info", "ldpc_b200_quantize", "ldpc_b200_decode", "ldpc_b200_decode_async", "ldpc_b200_sync",
-           "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_decode_device", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
+           "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
            "ldpc_b200_awgn_device", "ldpc_b200_awgn", "ldpc_b200_count_errors_device"]
 
 

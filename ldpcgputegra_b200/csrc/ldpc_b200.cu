@@ -620,6 +620,21 @@ int ldpc_b200_host_alloc(void** p, size_t bytes)
 }
 int ldpc_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LDPC_OK : LDPC_ERR_CUDA; }
 
+int ldpc_b200_device_alloc(ldpc_handle h, void** p, size_t bytes)
+{
+    if (!h || !p) return fail(h, LDPC_ERR_INVALID, "device_alloc: bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(h, LDPC_ERR_NOMEM, "device_alloc: cudaMalloc failed"); }
+    return LDPC_OK;
+}
+int ldpc_b200_device_free(ldpc_handle h, void* p)
+{
+    if (!h) return LDPC_ERR_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaFree(p));
+    return LDPC_OK;
+}
+
 int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters_done, void* cuda_stream)
 {
     if (!h || !d_llr || !d_hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode_device: bad argument");
