@@ -109,20 +109,21 @@ __device__ __forceinline__ void gp_constants(const GpMode& md, float min1, float
 
 // One check row for one frame, degree known at compile time: contributions stay in registers.  WRITE_V = layered (posteriors
 // updated in place).
+// (state pointers, stride and mode are passed one by one, not as a struct: the on-chip engine calls this with shared-memory
+// pointers held in registers, and the mode must stay a kernel parameter in the constant bank)
 template <class S, int D, bool WRITE_V>
-__device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int cls, bool first)
+__device__ __forceinline__ void gp_row(const GpMode& md, S* V, S* MSG, const uint32_t* pos, int T, int t, size_t e, int cls, bool first)
 {
-    const GpMode& md = A.md;
     float x[D], a[D];
     uint32_t idx[D];
     float min1 = md.min_init, min2 = md.min_init;
     int par = 0;
 #pragma unroll
-    for (int j = 0; j < D; j++) idx[j] = __ldg(A.pos + e + j);
+    for (int j = 0; j < D; j++) idx[j] = __ldg(pos + e + j);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const float v = GpIO<S>::ld(A.V + (size_t)idx[j] * A.T + t);
-        const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
+        const float v = GpIO<S>::ld(V + (size_t)idx[j] * T + t);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
         float xx = __fsub_rn(v, m);
         if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
         x[j] = xx;
@@ -141,11 +142,11 @@ __device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int 
         const float mag = (a[j] == min1) ? c1 : c2;
         const int flag = md.x86 ? (x[j] < 0.0f) : (x[j] > 0.0f);
         const float msg = (par ^ flag ^ k) ? -mag : mag;
-        GpIO<S>::st(A.MSG + (e + j) * A.T + t, msg);
+        GpIO<S>::st(MSG + (e + j) * T + t, msg);
         if (WRITE_V) {
             float vn = __fadd_rn(x[j], msg);
             if (!md.is_float) vn = gp_clamp(vn, md.lo, md.hi);
-            GpIO<S>::st(A.V + (size_t)idx[j] * A.T + t, vn);
+            GpIO<S>::st(V + (size_t)idx[j] * T + t, vn);
         }
     }
 }
@@ -153,15 +154,14 @@ __device__ __forceinline__ void gp_row(const GpArgs<S>& A, int t, size_t e, int 
 // run-time degree (rows wider than 8: 2048x384 has degree 32, DVB-S2 rate 1/9 degree 27): two passes, the contributions are
 // recomputed from memory in the second one (L1/L2 hits) instead of being parked in local memory
 template <class S, bool WRITE_V>
-__device__ __noinline__ void gp_row_rt(const GpArgs<S>& A, int t, size_t e, int D, int cls, bool first)
+__device__ __noinline__ void gp_row_rt(const GpMode& md, S* V, S* MSG, const uint32_t* pos, int T, int t, size_t e, int D, int cls, bool first)
 {
-    const GpMode& md = A.md;
     float min1 = md.min_init, min2 = md.min_init;
     int par = 0;
 #pragma unroll 1
     for (int j = 0; j < D; j++) {
-        const float v = GpIO<S>::ld(A.V + (size_t)__ldg(A.pos + e + j) * A.T + t);
-        const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
+        const float v = GpIO<S>::ld(V + (size_t)__ldg(pos + e + j) * T + t);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
         float xx = __fsub_rn(v, m);
         if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
         const float aa = gp_magnitude(md, xx, cls);
@@ -175,19 +175,19 @@ __device__ __noinline__ void gp_row_rt(const GpArgs<S>& A, int t, size_t e, int 
     const int k = md.x86 ? (D & 1) : 1;
 #pragma unroll 1
     for (int j = 0; j < D; j++) {
-        const size_t vi = (size_t)__ldg(A.pos + e + j) * A.T + t;
-        const float v = GpIO<S>::ld(A.V + vi);
-        const float m = first ? 0.0f : GpIO<S>::ld(A.MSG + (e + j) * A.T + t);
+        const size_t vi = (size_t)__ldg(pos + e + j) * T + t;
+        const float v = GpIO<S>::ld(V + vi);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
         float xx = __fsub_rn(v, m);
         if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
         const float mag = (gp_magnitude(md, xx, cls) == min1) ? c1 : c2;
         const int flag = md.x86 ? (xx < 0.0f) : (xx > 0.0f);
         const float msg = (par ^ flag ^ k) ? -mag : mag;
-        GpIO<S>::st(A.MSG + (e + j) * A.T + t, msg);
+        GpIO<S>::st(MSG + (e + j) * T + t, msg);
         if (WRITE_V) {
             float vn = __fadd_rn(xx, msg);
             if (!md.is_float) vn = gp_clamp(vn, md.lo, md.hi);
-            GpIO<S>::st(A.V + vi, vn);
+            GpIO<S>::st(V + vi, vn);
         }
     }
 }
@@ -198,11 +198,11 @@ __device__ __forceinline__ void gp_all_rows(const GpArgs<S>& A, int t, bool firs
     size_t e = 0;
     for (int c = 0; c < A.nb_deg; c++) {
         const int D = A.deg[c], R = A.rows[c];
-#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V>(A, t, e, c, first); break;
+#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V>(A.md, A.V, A.MSG, A.pos, A.T, t, e, c, first); break;
         switch (D) {
             GP_CASE(3) GP_CASE(4) GP_CASE(5) GP_CASE(6) GP_CASE(7) GP_CASE(8)
         default:
-            for (int r = 0; r < R; r++, e += D) gp_row_rt<S, WRITE_V>(A, t, e, D, c, first);
+            for (int r = 0; r < R; r++, e += D) gp_row_rt<S, WRITE_V>(A.md, A.V, A.MSG, A.pos, A.T, t, e, D, c, first);
         }
 #undef GP_CASE
     }

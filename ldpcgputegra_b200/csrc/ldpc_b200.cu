@@ -20,6 +20,7 @@
 #include "channel.cuh"
 #include "launch.cuh"
 #include "kernel_gp.cuh"
+#include "kernel_oc.cuh"
 
 using namespace ldpcb200;
 
@@ -50,6 +51,7 @@ struct ldpc_b200_handle_s {
     int elem = 1;                   // bytes per LLR / posterior / message element at the boundary (1, 2 or 4)
     GpMode gp_mode{};
     int32_t* d_cptr = nullptr; int32_t* d_cedge = nullptr;
+    OcRow* d_oc_rows = nullptr; int32_t* d_oc_levels = nullptr; int oc_nlevels = 0, oc_F = 0, oc_threads = 0; size_t oc_smem = 0;   // on-chip generic engine (kernel 5)
     int levels = 0, sms = 0;
     // row-parallel plan
     int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0; size_t rp_smem = 0;
@@ -96,10 +98,10 @@ int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& w
     if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
     if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
     if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
-    if (p->kernel < 0 || p->kernel > 4) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
+    if (p->kernel < 0 || p->kernel > 5) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
     const bool generic = p->dtype != LDPC_DTYPE_I8 || p->schedule != LDPC_SCHED_LAYERED;
     if (generic && (p->kernel == 1 || p->kernel == 2 || p->kernel == 4)) { why = "kernels 1, 2 and 4 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
-    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
+    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3 || p->kernel == 5)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
     if (p->dtype == LDPC_DTYPE_F32) {
         if (p->algo == LDPC_ALGO_OMS && (p->offset < 0 || p->llr_scale <= 0)) { why = "float OMS: offset >= 0 and llr_scale > 0 (offset is offset/llr_scale in channel units)"; return LDPC_ERR_INVALID; }
         if ((p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS) && !(p->factor1 > 0.0f && p->factor2 > 0.0f)) { why = "float NMS: factors must be positive"; return LDPC_ERR_INVALID; }
@@ -291,7 +293,7 @@ void destroy_impl(ldpc_handle h)
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
     cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2);
-    cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge);
+    cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge); cudaFree(h->d_oc_rows); cudaFree(h->d_oc_levels);
     free(h->code.pos);
     delete h;
 }
@@ -350,11 +352,37 @@ int launch_decode_gp(ldpc_handle h, Slot& s, const void* d_llr, uint8_t* d_hard,
     return LDPC_OK;
 }
 
+// generic engine, on-chip state: frame-major in, hard decisions out, nothing else touches HBM
+template <class S>
+int launch_decode_oc(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
+{
+    const ldpc_code_t& c = h->code;
+    OcArgs<S> a{};
+    a.llr = reinterpret_cast<const S*>(d_llr); a.hard = d_hard; a.iters_done = d_iters;
+    a.dbg_post = want_debug ? reinterpret_cast<S*>(h->d_dbg_post) : nullptr; a.dbg_msgs = want_debug ? reinterpret_cast<S*>(h->d_dbg_msgs) : nullptr;
+    a.pos = h->d_pos; a.cptr = h->d_cptr; a.cedge = h->d_cedge; a.rows = h->d_oc_rows; a.level_ptr = h->d_oc_levels;
+    a.frames = frames; a.n = c.n; a.m = c.m; a.n_checks = c.n_checks; a.nlevels = h->oc_nlevels; a.F = h->oc_F; a.iters = iters;
+    a.flooding = h->prm.schedule == LDPC_SCHED_FLOODING; a.et = h->prm.early_term == LDPC_ET_SYNDROME;
+    a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.md = h->gp_mode;
+    const int blocks = (int)std::min<size_t>((size_t)h->sms, (frames + h->oc_F - 1) / h->oc_F);
+    CU_TRY(h, cudaFuncSetAttribute(oc_decode_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->oc_smem));
+    a.threads = h->oc_threads;
+    oc_decode_kernel<S><<<blocks, h->oc_threads, h->oc_smem, st>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return LDPC_OK;
+}
+
 // decode `frames` frames that are already in device memory, on stream st.  For the frame-parallel kernel the slot's V/MSG
 // state is used, `frames` must fit it.
 int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
 {
     const ldpc_code_t& c = h->code;
+    if (h->kernel == 5) {
+        if (h->elem == 4) return launch_decode_oc<float>(h, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        if (h->elem == 2) return launch_decode_oc<int16_t>(h, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        return launch_decode_oc<int8_t>(h, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+    }
     if (h->kernel == 3) {
         if (h->elem == 4) return launch_decode_gp<float>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
         if (h->elem == 2) return launch_decode_gp<int16_t>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
@@ -502,7 +530,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
 
     // kernel selection.  int16 / float / flooding -> the generic engine; int8 layered -> the on-chip row-parallel kernel when the
     // whole state of >= 8 frame pairs per SM fits in shared memory, else the frame-parallel kernel
-    const bool generic = params->dtype != LDPC_DTYPE_I8 || params->schedule != LDPC_SCHED_LAYERED || params->kernel == 3;
+    const bool generic = params->dtype != LDPC_DTYPE_I8 || params->schedule != LDPC_SCHED_LAYERED || params->kernel == 3 || params->kernel == 5;
     h->elem = params->dtype == LDPC_DTYPE_F32 ? 4 : (params->dtype == LDPC_DTYPE_I16 ? 2 : 1);
     h->kernel = generic ? 3 : 1;
     if (generic) {
@@ -516,6 +544,43 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         CREATE_TRY(cudaMemcpy(h->d_cptr, cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMalloc((void**)&h->d_cedge, cedge.size() * sizeof(int32_t)));
         CREATE_TRY(cudaMemcpy(h->d_cedge, cedge.data(), cedge.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        // on-chip variant (kernel 5): fp32 state of F frames in shared memory, rows in level order (flooding: one level)
+        const bool flooding = params->schedule == LDPC_SCHED_FLOODING;
+        const size_t per_frame = (size_t)(code->n + code->m + (flooding ? code->n : 0)) * sizeof(float);
+        const int F = (int)std::min<size_t>(OC_MAXF, ((size_t)prop.sharedMemPerBlockOptin - 1024) / per_frame);
+        if (params->kernel == 5 && F < 1) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the on-chip generic engine"); }
+        if ((params->kernel == 5 && F >= 1) || (params->kernel == 0 && F >= 8)) {
+            std::vector<int32_t> level(code->n_checks, 0);
+            int levels = 1;
+            if (!flooding) { levels = ldpc_b200_level_schedule(code, level.data()); if (levels < 0) { destroy_impl(h); return fail(nullptr, levels, "level schedule failed"); } }
+            h->levels = levels;
+            std::vector<OcRow> rows_ref((size_t)code->n_checks), rows_sorted;
+            { int r = 0; uint32_t e = 0;
+              for (int k = 0; k < code->nb_deg; k++) for (int q = 0; q < code->rows[k]; q++, r++) { rows_ref[r] = OcRow{ e, (uint16_t)code->deg[k], (uint16_t)k }; e += code->deg[k]; } }
+            std::vector<int32_t> level_ptr((size_t)levels + 1, 0);
+            for (int r = 0; r < code->n_checks; r++) level_ptr[level[r] + 1]++;
+            for (int L = 0; L < levels; L++) level_ptr[L + 1] += level_ptr[L];
+            rows_sorted.resize(code->n_checks);
+            { std::vector<int32_t> fill(level_ptr.begin(), level_ptr.end() - 1);
+              for (int r = 0; r < code->n_checks; r++) rows_sorted[fill[level[r]]++] = rows_ref[r]; }     // stable: reference order inside a level, same-degree rows adjacent
+            CREATE_TRY(cudaMalloc((void**)&h->d_oc_rows, rows_sorted.size() * sizeof(OcRow)));
+            CREATE_TRY(cudaMemcpy(h->d_oc_rows, rows_sorted.data(), rows_sorted.size() * sizeof(OcRow), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc((void**)&h->d_oc_levels, level_ptr.size() * sizeof(int32_t)));
+            CREATE_TRY(cudaMemcpy(h->d_oc_levels, level_ptr.data(), level_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            h->kernel = 5; h->oc_nlevels = levels; h->oc_F = F; h->oc_smem = per_frame * F;
+            // CTA size.  A round of (row, frame) tasks costs max(latency of one task, issue time of the round); the first measurement
+            // (T chosen to minimise idle lanes -> 128 threads) was 3x slower than a fixed 512 because short rounds are latency-
+            // bound: model a task as ~600 cycles alone and ~2 cycles of issue slots per thread, and minimise the sum over levels.
+            auto round_cost = [](long tasks) { return std::max(600.0, 2.0 * (double)tasks); };
+            double best_cost = 1e300;
+            for (int T = 128; T <= OC_MAX_THREADS; T += 32) {
+                double cost = 0;
+                auto add = [&](long tasks) { cost += (double)(tasks / T) * round_cost(T) + (tasks % T ? round_cost(tasks % T) : 0.0); };
+                for (int L = 0; L < levels; L++) add((long)(level_ptr[L + 1] - level_ptr[L]) * F);
+                if (flooding) add((long)code->n * F);
+                if (cost < best_cost) { best_cost = cost; h->oc_threads = T; }
+            }
+        }
     }
     if (!generic && code->n <= 16383 && params->kernel != 1 && params->kernel != 4) {
         RpPlan plan;
@@ -584,8 +649,8 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     // pipeline granularity of decode(): whole waves of the chosen kernel.  H2D, kernel and D2H take about the same time per
     // frame for 576x288 over PCIe Gen5, so the fill/drain of the 3-stage pipeline costs 2 chunks: many small chunks win
     // (measured: 5 chunks 1.17 ms, 10 chunks of one wave each — see profiles/r01_e2e_chunks.txt).  reserved[2] overrides (waves per chunk).
-    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
-    size_t k = h->kernel == 2 ? 1 : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
+    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : h->kernel == 5 ? (size_t)h->sms * h->oc_F : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
+    size_t k = h->kernel == 2 ? 1 : h->kernel == 5 ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
     *out = h;
@@ -600,8 +665,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     switch (what) {
     case LDPC_INFO_KERNEL: *value = h->kernel; break;
     case LDPC_INFO_LEVELS: *value = h->levels; break;
-    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : (h->kernel == 1 ? 16384 : 0); break;
-    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : (h->kernel == 4 ? FS_CONSUMERS * 4 : FP_BLOCK * 4)); break;
+    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : h->kernel == 5 ? (int64_t)h->oc_smem : (h->kernel == 1 ? 16384 : 0); break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : h->kernel == 5 ? h->oc_F : (h->kernel == 4 ? FS_CONSUMERS * 4 : FP_BLOCK * 4)); break;
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;
@@ -658,7 +723,7 @@ int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* ha
     if ((rc = ensure(h, &s.d_hard, &s.hard_bytes, frames * hb))) return rc;
     uint8_t* d_it = nullptr;
     if (iters_done) {
-        if (h->kernel == 2) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
+        if (h->kernel == 2 || h->kernel == 5) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
         else if (h->kernel == 3) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (frames + 31) / 32 * 32))) return rc; d_it = s.d_iters; }
         else { const size_t tq = h->kernel == 4 ? FS_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
     }

@@ -1,5 +1,6 @@
-"""GPU suite, generic engine (kernel 3: one frame per thread, fp32 arithmetic): int16 storage, float min-sum, the flooding
-schedule — and int8 layered in all four reference semantics, which pins this engine to the reference-checked oracle.
+"""GPU suite, generic engine (fp32 arithmetic; kernel 3 = one frame per thread with the state in HBM, kernel 5 = (row, frame)
+tasks with the state in shared memory): int16 storage, float min-sum, the flooding schedule — and int8 layered in all four
+reference semantics, which pins this engine to the reference-checked oracle.
 Integer modes are bit-exact (hard decisions, posteriors, messages, iteration counts).  The float mode issues the oracle's
 operations in the oracle's order, so it is compared bit-for-bit too; the stated tolerance of the float path is therefore 0 ulp
 against oracle/ldpc_oracle.c (which is this project's own definition: no float decoder exists in the reference — parity unpinned)."""
@@ -15,14 +16,17 @@ COMBOS = [("X86_SSE", "OMS"), ("X86_SSE", "NMS"), ("UNIFORM", "OMS"), ("UNIFORM"
           ("GPU_FIXED", "MS"), ("GPU_FIXED", "OMS"), ("GPU_FIXED", "NMS"), ("GPU_FIXED", "2NMS")]
 
 
-def gpu_decode(code, llr, iters, **kw):
-    dec = pkg.CGPUDecoder(code, nb_frames=max(llr.shape[0], 1), device=0, **kw)
+ENGINES = [5, 3]
+
+
+def gpu_decode(code, llr, iters, kernel=0, **kw):
+    dec = pkg.CGPUDecoder(code, nb_frames=max(llr.shape[0], 1), device=0, kernel=kernel, **kw)
     dec.set_debug(True)
     hard, it = dec.decode(llr, iters, want_iters=True)
     post, msgs = dec.debug_state(llr.shape[0])
     k, prm = dec.info(pkg.INFO_KERNEL), dec.params
     dec.close()
-    assert k == 3
+    assert k == (kernel or k) and k in (3, 5)
     return dict(hard=hard, post=post, msgs=msgs, iters=it, prm=prm)
 
 
@@ -39,44 +43,51 @@ def float_llr(code, frames, ebn0, seed):
     return (-1.0 + sigma * rng.standard_normal((frames, code.n))).astype(np.float32)
 
 
+@pytest.mark.parametrize("kernel", ENGINES)
 @pytest.mark.parametrize("sem,algo", COMBOS)
-def test_int8_layered_pins_generic_engine(code576, sem, algo):
+def test_int8_layered_pins_generic_engine(code576, sem, algo, kernel):
     llr = np.concatenate([awgn_llr(code576, 200, 2.0, 141), stress_llr(code576, 150, 143), stress_llr(code576, 101, 144, full_range=True)])
     for iters in (1, 10):
-        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=3)
-        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"{sem}/{algo}/I{iters}")
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=kernel)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"{sem}/{algo}/I{iters}/k{kernel}")
+    if kernel == 5:      # early termination of the fixed-point layered schedule through the on-chip engine (extrinsic-sign criterion)
+        g = gpu_decode(code576, llr, 30, algo=algo, semantics=sem, kernel=5, early_term=1)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, 30), f"{sem}/{algo}/ET/k5")
 
 
+@pytest.mark.parametrize("kernel", ENGINES)
 @pytest.mark.parametrize("sem,algo", COMBOS)
-def test_int8_flooding(code576, sem, algo):
+def test_int8_flooding(code576, sem, algo, kernel):
     llr = np.concatenate([awgn_llr(code576, 200, 2.0, 151), stress_llr(code576, 133, 153, full_range=(sem == "GPU_FIXED"))])
     for iters, et in ((1, 0), (10, 0), (30, 1)):
-        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, schedule="FLOODING", early_term=et)
-        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"flooding {sem}/{algo}/I{iters}/et{et}")
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, schedule="FLOODING", early_term=et, kernel=kernel)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"flooding {sem}/{algo}/I{iters}/et{et}/k{kernel}")
     assert g["iters"].min() < 30
 
 
+@pytest.mark.parametrize("kernel", ENGINES)
 @pytest.mark.parametrize("schedule", ["LAYERED", "FLOODING"])
 @pytest.mark.parametrize("kw", [dict(semantics="ARM_SCALAR", algo="OMS", sat_var=32767, sat_msg=8191, offset=16),
                                 dict(semantics="ARM_SCALAR", algo="OMS", sat_var=2047, sat_msg=511, offset=8),
                                 dict(semantics="UNIFORM", algo="OMS", sat_var=32767, sat_msg=4095, offset=16),
                                 dict(semantics="UNIFORM", algo="NMS", sat_var=8191, sat_msg=2047, factor_q5=29)])
-def test_int16(code576, schedule, kw):
+def test_int16(code576, schedule, kw, kernel):
     q8 = np.concatenate([awgn_llr(code576, 200, 1.5, 161), stress_llr(code576, 120, 163)]).astype(np.int16)
     llr = (q8 * 16 + (np.arange(q8.size).reshape(q8.shape) % 13 - 6)).astype(np.int16)     # 16x finer grid, not multiples of 16
     llr[5] = np.clip(llr[5].astype(np.int32) * 40, -32768, 32767).astype(np.int16)         # drives the rails
     for iters, et in ((2, 0), (10, 0), (25, 1)):
-        g = gpu_decode(code576, llr, iters, dtype="I16", schedule=schedule, early_term=et, **kw)
-        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"int16 {schedule} {kw} I{iters} et{et}")
+        g = gpu_decode(code576, llr, iters, dtype="I16", schedule=schedule, early_term=et, kernel=kernel, **kw)
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"int16 {schedule} {kw} I{iters} et{et} k{kernel}")
 
 
+@pytest.mark.parametrize("kernel", ENGINES)
 @pytest.mark.parametrize("schedule", ["FLOODING", "LAYERED"])
 @pytest.mark.parametrize("kw", [dict(algo="NMS", factor1=0.75), dict(algo="2NMS", factor1=0.75, factor2=0.875), dict(algo="MS"),
                                 dict(algo="OMS", offset=1), dict(algo="NMS", factor1=0.8125)])
-def test_float_min_sum(code576, schedule, kw):
+def test_float_min_sum(code576, schedule, kw, kernel):
     llr = np.concatenate([float_llr(code576, 150, 2.0, 171), float_llr(code576, 100, 0.5, 172), float_llr(code576, 51, 4.0, 173)])
     for iters, et in ((1, 0), (10, 0), (40, 1)):
-        g = gpu_decode(code576, llr, iters, dtype="F32", schedule=schedule, early_term=et, **kw)
+        g = gpu_decode(code576, llr, iters, dtype="F32", schedule=schedule, early_term=et, kernel=kernel, **kw)
         o = oracle_decode_float(code576, g["prm"], llr, iters)
         # tolerance: 0 (same operations in the same order); hard decisions identical
         assert_same(g, o, f"float {schedule} {kw} I{iters} et{et}")
@@ -88,19 +99,20 @@ def test_generic_engine_other_codes(built, name):
     """degree 32 rows (2048x384: the run-time-degree path), column degree up to 15 (1200x600), N % 32 != 0 (200x100)"""
     code = Code.load(name)
     llr8 = awgn_llr(code, 70, 2.5, 181)
-    g = gpu_decode(code, llr8, 5, algo="OMS", semantics="X86_SSE", kernel=3)
-    assert_same(g, oracle_decode(code, g["prm"], llr8, 5), name + " int8 layered")
-    g = gpu_decode(code, llr8, 5, algo="NMS", semantics="UNIFORM", schedule="FLOODING")
-    assert_same(g, oracle_decode(code, g["prm"], llr8, 5), name + " int8 flooding")
     y = float_llr(code, 70, 2.5, 182)
-    g = gpu_decode(code, y, 6, dtype="F32", algo="NMS", schedule="FLOODING", early_term=1)
-    assert_same(g, oracle_decode_float(code, g["prm"], y, 6), name + " float flooding")
+    for kernel in ENGINES:
+        g = gpu_decode(code, llr8, 5, algo="OMS", semantics="X86_SSE", kernel=kernel)
+        assert_same(g, oracle_decode(code, g["prm"], llr8, 5), f"{name} int8 layered k{kernel}")
+        g = gpu_decode(code, llr8, 5, algo="NMS", semantics="UNIFORM", schedule="FLOODING", kernel=kernel)
+        assert_same(g, oracle_decode(code, g["prm"], llr8, 5), f"{name} int8 flooding k{kernel}")
+        g = gpu_decode(code, y, 6, dtype="F32", algo="NMS", schedule="FLOODING", early_term=1, kernel=kernel)
+        assert_same(g, oracle_decode_float(code, g["prm"], y, 6), f"{name} float flooding k{kernel}")
 
 
 def test_generic_ragged_packed_and_device_channel(code576):
     y = float_llr(code576, 45, 3.0, 191)
-    for frames in (0, 1, 31, 45):
-        dec = pkg.CGPUDecoder(code576, nb_frames=64, device=0, dtype="F32", algo="NMS", schedule="FLOODING", out_format=1)
+    for frames, kernel in ((0, 5), (1, 5), (31, 5), (45, 5), (45, 3), (1, 3)):
+        dec = pkg.CGPUDecoder(code576, nb_frames=64, device=0, dtype="F32", algo="NMS", schedule="FLOODING", out_format=1, kernel=kernel)
         packed = dec.decode(y[:frames], 8)
         ref = oracle_decode_float(code576, dec.params, y[:frames], 8)["hard"]
         assert np.array_equal(np.unpackbits(packed, axis=1, bitorder="little")[:, :code576.n] if frames else packed.reshape(0, code576.n), ref)
