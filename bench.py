@@ -268,6 +268,21 @@ def main():
     e2e_fps = world * F * steps / e2e_s
     host_fe = int(h_hard.array[:, :k_info].any(axis=1).sum())
 
+    # the same call with bit-packed output (the new 1-bit-per-bit format: D2H is 8x smaller) — reported beside the headline e2e
+    decp = pkg.CGPUDecoder(code, nb_frames=F, device=local_rank, out_format=1)
+    h_pack = pkg.PinnedArray((F, (n + 7) // 8), np.uint8)
+    for i in range(3):
+        decp.decode(h_llr[i % 2].array, ITERS, out=h_pack.array)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        decp.decode(h_llr[i % 2].array, ITERS, out=h_pack.array)
+    torch.cuda.synchronize()
+    e2e_packed_fps = world * F * steps / max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    packed_ok = bool(np.array_equal(np.unpackbits(h_pack.array, axis=1, bitorder="little")[:, :n], dec.decode(h_llr[(steps - 1) % 2].array, ITERS)))
+    decp.close()
+
     hbm_peak, sm_max_mhz, peak_src = peaks()
     traffic = ncu_traffic() if F == FRAMES else None
     bytes_per_frame = n + n                      # int8 LLR in + one byte per bit out (the reference's output format)
@@ -287,7 +302,9 @@ def main():
                             "edge_updates_per_s": per_gpu_fps * ITERS * m, "ops_per_edge_update": 18,
                             "note": "canonical scalar-int cost of SURVEY 8d; two frames per instruction (f16x2) may exceed 1.0"},
             "e2e": {"value": e2e_fps * k_info / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": F * n, "d2h_bytes_per_step": F * n,
-                    "frames_per_s": e2e_fps, "api": "ldpc_b200_decode (blocking, pinned host buffers, 4 stream slots)"},
+                    "frames_per_s": e2e_fps, "api": "ldpc_b200_decode (blocking, pinned host buffers, 4 stream slots)",
+                    "bound": "PCIe: 37.7 MB each way per step; this box moves 41.7 GB/s per direction when both are busy (tools/pcie_probe.py) = 20.8 Gb/s",
+                    "packed_output": {"value": e2e_packed_fps * k_info / 1e9, "unit": "Gb/s", "d2h_bytes_per_step": F * ((n + 7) // 8), "equals_byte_output": packed_ok}},
             "gpu_launches": int(launches), "kernel": {1: "frame-parallel (HBM state)", 2: "row-parallel on-chip", 3: "generic engine", 4: "frame-parallel, bulk-copy staged"}[kernel],
             "clocks": clocks, "frames_per_s": fps, "air_gbps": fps * n / 1e9,
             "ber_fer": {"frames": F, "bit_errors": be, "frame_errors": fe, "fer": fe / F, "e2e_frame_errors_last_batch": host_fe}}
