@@ -131,7 +131,7 @@ static inline int rail_lo(const oparams* p) { return p->sem == LDPC_SEM_GPU_FIXE
 static inline int rail_hi(const oparams* p) { return (p->sem == LDPC_SEM_ARM_SCALAR || p->wide) ? p->sat_var : 127; }
 
 /* one check row: contributions from (v, m), new messages into m; posteriors written back only when `write_v` (layered). */
-static inline void update_row(const ldpc_code_t* code, const oparams* p, int* v, int* m, int e, int d, int c, int first_iter, int write_v)
+static inline int update_row(const ldpc_code_t* code, const oparams* p, int* v, int* m, int e, int d, int c, int first_iter, int write_v)
 {
     const uint32_t* pos = code->pos;
     const int wide = p->wide;
@@ -177,6 +177,7 @@ static inline void update_row(const ldpc_code_t* code, const oparams* p, int* v,
         if (write_v) v[pos[e + j]] = vn;
         m[e + j] = msg;
     }
+    return par;       /* XOR of the row's flags as seen by this update (GPU_FIXED: of (x > 0)) */
 }
 
 /* decode ONE frame held in int arrays v[n] (in: LLR, out: posterior) and m[M] (out: messages). Returns iterations run.

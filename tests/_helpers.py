@@ -141,6 +141,38 @@ def ref_x86_decode(L, algo: str, param: int, llr: np.ndarray, iters: int):
     return dict(hard=hard, post=post, msgs=msgs)
 
 
+def ref_gpu(code_name: str):
+    """The reference's own gpu_fixed kernels cross-compiled for sm_100a (oracle/_ref/libref_gpu_<code>.so); needs a GPU to run."""
+    p = REF_DIR / f"libref_gpu_{code_name}.so"
+    if not p.exists():
+        return None
+    L = C.CDLL(str(p))
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    L.ref_gpu_info.argtypes = [C.POINTER(C.c_int)]
+    L.ref_gpu_table.argtypes = [vp]
+    L.ref_gpu_decode.restype = i32
+    L.ref_gpu_decode.argtypes = [i32, vp, vp, vp, vp, sz, i32, C.POINTER(C.c_float)]
+    return L
+
+
+def ref_gpu_decode(L, algo: str, llr: np.ndarray, iters: int, want_state=True):
+    """Runs the reference kernel launch sequence (H2D, Interleaver_uint8, LDPC_Sched_Stage_1_*_SIMD, InvInterleaver_uint8, D2H).
+    Returns dict(hard, post, msgs, kernel_ms, total_ms).  frames % 512 == 0."""
+    llr = np.ascontiguousarray(llr, np.int8)
+    F, n = llr.shape
+    info = (C.c_int * 4)(); L.ref_gpu_info(info)
+    assert n == info[0] and F % 512 == 0
+    hard = np.empty((F, n), np.uint8)
+    post = np.empty((F, n), np.int8) if want_state else None
+    msgs = np.empty((F, info[2]), np.int8) if want_state else None
+    ms = (C.c_float * 2)()
+    rc = L.ref_gpu_decode(ALGO[algo], llr.ctypes.data, hard.ctypes.data, post.ctypes.data if want_state else None,
+                          msgs.ctypes.data if want_state else None, F, iters, ms)
+    if rc:
+        raise RuntimeError(f"ref_gpu_decode -> {rc}")
+    return dict(hard=hard, post=post, msgs=msgs, kernel_ms=float(ms[0]), total_ms=float(ms[1]))
+
+
 def ref_arm(code_name: str):
     p = REF_DIR / f"libref_arm_{code_name}.so"
     if not p.exists():

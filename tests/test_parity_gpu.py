@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import ldpcgputegra_b200 as pkg
-from _helpers import Code, default_params, oracle_decode, oracle_quantize, oracle_pack, awgn_llr, stress_llr, ROOT
+from _helpers import (Code, default_params, oracle_decode, oracle_quantize, oracle_pack, awgn_llr, stress_llr, ROOT,
+                      ref_gpu, ref_gpu_decode)
 
 pytestmark = pytest.mark.gpu
 GOLD = ROOT / "tests" / "golden"
@@ -236,3 +237,34 @@ def test_async_slots_overlap_and_agree(code576):
         o = oracle_decode(code576, dec.params, src[s].array[:256], 10, want_state=False)
         assert np.array_equal(dst[s].array[:256], o["hard"])
     dec.close()
+
+
+@pytest.mark.parametrize("name", ["576x288", "1200x600", "2304x1152"])
+def test_reference_gpu_kernels(built, name):
+    """K6 of SURVEY 8c: the reference's OWN gpu_fixed kernels (LDPC_Sched_Stage_1_{MS,OMS,NMS,2NMS}_SIMD + (Inv)Interleaver_uint8,
+    unmodified, cross-compiled for sm_100a into oracle/_ref) run on this GPU; the oracle's GPU_FIXED mode and this library's
+    GPU_FIXED kernels must reproduce their hard decisions, posteriors and messages bit for bit — which pins that mode."""
+    L = ref_gpu(name)
+    if L is None:
+        pytest.skip("oracle/_ref/libref_gpu_*.so not built (needs /root/reference at build time)")
+    c = Code.load(name)
+    llr = np.concatenate([awgn_llr(c, 512, 2.0, 301), awgn_llr(c, 256, 0.5, 302), stress_llr(c, 256, 303, full_range=True)])
+    for algo in ("MS", "OMS", "NMS"):
+        for iters in (1, 3, 10):
+            r = ref_gpu_decode(L, algo, llr, iters)
+            prm = default_params(algo=algo, semantics="GPU_FIXED")
+            o = oracle_decode(c, prm, llr, iters)
+            for k in ("hard", "post", "msgs"):
+                assert np.array_equal(r[k], o[k]), f"{name} {algo} I{iters}: oracle GPU_FIXED differs from the reference kernel in {k} ({(r[k] != o[k]).sum()})"
+        g = gpu_decode(c, llr, 10, algo=algo, semantics="GPU_FIXED")
+        for k in ("hard", "post", "msgs"):
+            assert np.array_equal(r[k], g[k]), f"{name} {algo}: this library differs from the reference kernel in {k}"
+    # 2NMS is compiled with EARLY_TERM 1 (CUDA_2NMS_SIMD.cu:17): lanes of a warp that satisfy the test `break` past __syncthreads
+    # calls the other lanes still execute (:286-291) — undefined behaviour that DEADLOCKS on sm_100 (observed: the kernel never
+    # returns for 2 or more iterations on AWGN frames).  It can therefore only be run for one iteration, where the loop is not
+    # entered; the 0.75 / 0.875 arithmetic it shares with NMS is pinned above.
+    r1 = ref_gpu_decode(L, "2NMS", llr, 1)
+    g1 = gpu_decode(c, llr, 1, algo="2NMS", semantics="GPU_FIXED")
+    o1 = oracle_decode(c, g1["prm"], llr, 1)
+    for k in ("hard", "post", "msgs"):
+        assert np.array_equal(r1[k], g1[k]) and np.array_equal(r1[k], o1[k]), f"{name} 2NMS I1 {k}"
