@@ -193,6 +193,26 @@ int  ldpc_b200_awgn(ldpc_handle h, void* llr_host, size_t frames, float sigma, u
 /* counts over the first (n - n_checks) positions of every frame, all-zero codeword assumed; out[0]=bit errors, out[1]=frame errors */
 int  ldpc_b200_count_errors_device(ldpc_handle h, const uint8_t* d_hard, size_t frames, uint64_t* out2_host, void* cuda_stream);
 
+/* systematic encoder derived from the parity-check table (ref: the `-encoder` option, code/x86/main_p.cpp:232-233,
+ * EncoderLibrary code/x86/CEncoder/EncoderLibrary.h, GenericEncoder::encode code/x86/CEncoder/GenericEncoder.cpp:38-78 — a DVB-S2
+ * IRA encoder driven by a second table; this one needs only H).  Information bits = the first n - n_checks positions, parity
+ * positions solved from H c = 0 (peeling, then a dense GF(2) inverse for what peeling cannot reach).  LDPC_ERR_UNSUPPORTED when
+ * the last n_checks columns of H are singular.  Bits are bytes in {0,1}, frame-major.  Runs on the GPU. */
+typedef struct ldpc_b200_encoder_s* ldpc_encoder;
+int  ldpc_b200_encoder_create(ldpc_encoder* e, const ldpc_code_t* code, int device);
+void ldpc_b200_encoder_destroy(ldpc_encoder e);
+const char* ldpc_b200_encoder_last_error(ldpc_encoder e);      /* nullable: last create() error of this thread */
+int  ldpc_b200_encoder_info(ldpc_encoder e, int* n_phases, int* dense_unknowns);
+int  ldpc_b200_encode(ldpc_encoder e, const uint8_t* info /*[frames][n - n_checks]*/, uint8_t* codeword /*[frames][n]*/, size_t frames);   /* host buffers */
+/* device buffers; d_info nullable = counter-based random information bits of (seed, first_frame), first_frame % 32 == 0
+ * (ref: rand()%2 in GenericEncoder.cpp:47-51) */
+int  ldpc_b200_encode_device(ldpc_encoder e, const uint8_t* d_info, uint8_t* d_codeword, size_t frames, uint64_t seed, uint64_t first_frame, void* cuda_stream);
+/* channel and counters for a transmitted codeword: BPSK 0 -> -1, 1 -> +1 (ref: CChanelAWGN_MKL.cpp:129-139), same noise stream as
+ * ldpc_b200_awgn_device for the same (seed, frame); errors counted against the codeword over the information part
+ * (ref: CErrorAnalyzer::generate, buf_en_bits, code/x86/CErrorAnalyzer/CErrorAnalyzer.cpp:123-137) */
+int  ldpc_b200_awgn_codeword_device(ldpc_handle h, void* d_llr, const uint8_t* d_codeword, size_t frames, float sigma, uint64_t seed, uint64_t first_frame, void* cuda_stream);
+int  ldpc_b200_count_errors_ref_device(ldpc_handle h, const uint8_t* d_hard, const uint8_t* d_codeword, size_t frames, uint64_t* out2_host, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

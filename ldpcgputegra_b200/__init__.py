@@ -103,6 +103,14 @@ def lib() -> C.CDLL:
         "ldpc_b200_awgn_device": (i32, [vp, vp, sz, C.c_float, u64, u64, vp]),
         "ldpc_b200_awgn": (i32, [vp, vp, sz, C.c_float, u64, u64]),
         "ldpc_b200_count_errors_device": (i32, [vp, vp, sz, C.POINTER(u64), vp]),
+        "ldpc_b200_encoder_create": (i32, [C.POINTER(vp), C.POINTER(CodeT), i32]),
+        "ldpc_b200_encoder_destroy": (None, [vp]),
+        "ldpc_b200_encoder_last_error": (C.c_char_p, [vp]),
+        "ldpc_b200_encoder_info": (i32, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "ldpc_b200_encode": (i32, [vp, vp, vp, sz]),
+        "ldpc_b200_encode_device": (i32, [vp, vp, vp, sz, u64, u64, vp]),
+        "ldpc_b200_awgn_codeword_device": (i32, [vp, vp, vp, sz, C.c_float, u64, u64, vp]),
+        "ldpc_b200_count_errors_ref_device": (i32, [vp, vp, vp, sz, C.POINTER(u64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -116,7 +124,9 @@ EXPORTS = ["ldpc_b200_abi_version", "ldpc_b200_device_count", "ldpc_b200_status_
            "ldpc_b200_free_code", "ldpc_b200_level_schedule", "ldpc_b200_create", "ldpc_b200_destroy", "ldpc_b200_last_error",
            "ldpc_b200_get_info", "ldpc_b200_quantize", "ldpc_b200_decode", "ldpc_b200_decode_async", "ldpc_b200_sync",
            "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
-           "ldpc_b200_awgn_device", "ldpc_b200_awgn", "ldpc_b200_count_errors_device"]
+           "ldpc_b200_awgn_device", "ldpc_b200_awgn", "ldpc_b200_count_errors_device",
+           "ldpc_b200_encoder_create", "ldpc_b200_encoder_destroy", "ldpc_b200_encoder_last_error", "ldpc_b200_encoder_info", "ldpc_b200_encode",
+           "ldpc_b200_encode_device", "ldpc_b200_awgn_codeword_device", "ldpc_b200_count_errors_ref_device"]
 
 
 def _check(status: int, handle=None):
@@ -315,10 +325,60 @@ class CGPUDecoder:
     def awgn_device(self, d_llr: int, frames: int, sigma: float, seed: int, first_frame: int = 0, stream: int = 0):
         _check(lib().ldpc_b200_awgn_device(self._h, d_llr, frames, sigma, seed, first_frame, stream or None), self._h)
 
+    def awgn_codeword_device(self, d_llr: int, d_codeword: int, frames: int, sigma: float, seed: int, first_frame: int = 0, stream: int = 0):
+        _check(lib().ldpc_b200_awgn_codeword_device(self._h, d_llr, d_codeword, frames, sigma, seed, first_frame, stream or None), self._h)
+
+    def count_errors_ref_device(self, d_hard: int, d_codeword: int, frames: int, stream: int = 0):
+        out = (C.c_uint64 * 2)()
+        _check(lib().ldpc_b200_count_errors_ref_device(self._h, d_hard, d_codeword, frames, out, stream or None), self._h)
+        return int(out[0]), int(out[1])
+
     def count_errors_device(self, d_hard: int, frames: int, stream: int = 0):
         out = (C.c_uint64 * 2)()
         _check(lib().ldpc_b200_count_errors_device(self._h, d_hard, frames, out, stream or None), self._h)
         return int(out[0]), int(out[1])
+
+
+class Encoder:
+    """Systematic encoder derived from H (ref: the `-encoder` option / GenericEncoder, code/x86/CEncoder/GenericEncoder.cpp:38-78)."""
+
+    def __init__(self, code: Code, device: int = 0):
+        self.code = code
+        self._e = C.c_void_p()
+        c = code.c_struct()
+        st = lib().ldpc_b200_encoder_create(C.byref(self._e), C.byref(c), device)
+        if st != OK:
+            raise LdpcError(st, (lib().ldpc_b200_encoder_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._e:
+            lib().ldpc_b200_encoder_destroy(self._e)
+            self._e = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a, b = C.c_int(), C.c_int()
+        lib().ldpc_b200_encoder_info(self._e, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def encode(self, info_bits: np.ndarray) -> np.ndarray:
+        info_bits = np.ascontiguousarray(info_bits, dtype=np.uint8)
+        frames = info_bits.shape[0]
+        cw = np.empty((frames, self.code.n), dtype=np.uint8)
+        st = lib().ldpc_b200_encode(self._e, info_bits.ctypes.data, cw.ctypes.data, frames)
+        if st != OK:
+            raise LdpcError(st, (lib().ldpc_b200_encoder_last_error(self._e) or b"").decode())
+        return cw
+
+    def encode_device(self, d_codeword: int, frames: int, seed: int = 0, first_frame: int = 0, d_info: int = 0, stream: int = 0):
+        st = lib().ldpc_b200_encode_device(self._e, d_info or None, d_codeword, frames, seed, first_frame, stream or None)
+        if st != OK:
+            raise LdpcError(st, (lib().ldpc_b200_encoder_last_error(self._e) or b"").decode())
 
 
 def CreateDecoder(type: str, arch: str, format: str, code: Code, nb_frames: int = 65536, device: int = 0,

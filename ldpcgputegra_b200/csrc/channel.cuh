@@ -23,7 +23,7 @@ __device__ __forceinline__ int quantize_one(float p, int sat)
     return min(v, sat);
 }
 
-__global__ void quantize_kernel(const float* __restrict__ y, int8_t* __restrict__ q, size_t count, float scale, int sat)
+static __global__ void quantize_kernel(const float* __restrict__ y, int8_t* __restrict__ q, size_t count, float scale, int sat)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         q[i] = (int8_t)quantize_one(__fmul_rn(scale, y[i]), sat);
@@ -79,7 +79,7 @@ __global__ void awgn_kernel(S* __restrict__ q, size_t frames, int n, float sigma
 }
 
 // one warp per frame; out[0] += bit errors, out[1] += frame errors
-__global__ void count_errors_kernel(const uint8_t* __restrict__ hard, size_t frames, int n, int k_info, int packed, unsigned long long* out)
+static __global__ void count_errors_kernel(const uint8_t* __restrict__ hard, size_t frames, int n, int k_info, int packed, unsigned long long* out)
 {
     const int lane = threadIdx.x & 31;
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;

@@ -841,4 +841,15 @@ int ldpc_b200_count_errors_device(ldpc_handle h, const uint8_t* d_hard, size_t f
     return LDPC_OK;
 }
 
+
+/* accessor for encoder.cu's channel / counter entry points (not part of the public header) */
+int ldpc_b200_internal_channel_params(ldpc_handle h, int* device, int* n, int* n_checks, int* elem, int* llr_scale, int* sat_llr, int* packed,
+                                      unsigned long long** d_counters, void** slot0_stream)
+{
+    if (!h) return LDPC_ERR_INVALID;
+    *device = h->device; *n = h->code.n; *n_checks = h->code.n_checks; *elem = h->elem; *llr_scale = h->prm.llr_scale; *sat_llr = h->prm.sat_llr;
+    *packed = h->prm.out_format == LDPC_OUT_PACKED; *d_counters = h->d_counters; *slot0_stream = (void*)h->slot[0].stream;
+    return LDPC_OK;
+}
+
 }  // extern "C"
