@@ -315,16 +315,12 @@ def main():
         cpu_fps, kind, sample, cpu_hard = cpu_reference_run(llr_host, 3.0, threads)
         line["cpu_baseline"] = {"value": cpu_fps * k_info / 1e9, "unit": "Gb/s", "cores": threads, "kind": kind, "sample": sample,
                                 "frames_per_s": cpu_fps, "agrees_with_gpu": bool(np.array_equal(cpu_hard, dec.decode(llr_host, ITERS)))}
-        # the kernel to beat: the reference's own gpu_fixed OMS kernel (unmodified, built for sm_100a into oracle/_ref), same frames
+        # the kernel to beat: the reference's own gpu_fixed OMS kernel (unmodified, built for sm_100a into oracle/_ref), same workload,
+        # in its own process so that nothing it does can touch this one's CUDA context
         try:
-            from _helpers import ref_gpu, ref_gpu_decode
-            Lg = ref_gpu(CODE)
-            if Lg is not None:
-                ref_gpu_decode(Lg, "OMS", llr_host[:4096], ITERS, want_state=False)                      # warm-up
-                rg = min((ref_gpu_decode(Lg, "OMS", llr_host, ITERS, want_state=False) for _ in range(3)), key=lambda r: r["kernel_ms"])
-                line["reference_gpu_kernel"] = {"what": "LDPC_Sched_Stage_1_OMS_SIMD (gpu_fixed, GPU_FIXED semantics) on this B200, decode kernel only / H2D..D2H",
-                                                "kernel_ms": rg["kernel_ms"], "total_ms": rg["total_ms"],
-                                                "info_gbps_kernel": F * k_info / rg["kernel_ms"] / 1e6, "info_gbps_total": F * k_info / rg["total_ms"] / 1e6}
+            import subprocess
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "ref_gpu_time.py"), CODE, str(F), str(ITERS)], capture_output=True, text=True, timeout=180)
+            line["reference_gpu_kernel"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"unavailable": (r.stderr or "no output")[-200:]}
         except Exception as e:          # the comparison is a courtesy, never a reason to lose the bench line
             line["reference_gpu_kernel"] = {"unavailable": str(e)[:200]}
     if rank == 0:

@@ -9,7 +9,7 @@
  * Philox channel generator; only three integers per batch come back to the host.  There is no CPU decode path here.
  *
  *   ldpc_sim -fixed|-float [reference options] [-code 576x288 | -header constantes_sse.h [-table constantes_decoder.h]]
- *            [-gpus n] [-frames n] [-flooding] [-early] [-int16] [-MS] [-2NMS] [-sse|-avx|-x86|-gpu] [-seed s] [-max-frames n]
+ *            [-gpus n] [-frames n] [-flooding] [-early] [-int16] [-MS] [-2NMS] [-sse|-avx|-x86|-gpu] [-seed s] [-max-frames n] [-encoder]
  */
 #include <math.h>
 #include <pthread.h>
@@ -27,7 +27,7 @@ typedef struct {
     double snr_min, snr_max, snr_pas;
     int fe_limit, timer_s, worst_case, ber_limit, fer_limit;
     double ber_limit_value, fer_limit_value;
-    int iters, gpus;
+    int iters, gpus, real_encoder;
     size_t frames, max_frames;
     uint64_t seed;
 } sim_t;
@@ -35,7 +35,7 @@ typedef struct {
 typedef struct {
     int gpu;
     ldpc_handle h;
-    void* d_llr; uint8_t* d_hard;
+    void* d_llr; uint8_t* d_hard; uint8_t* d_cw; ldpc_encoder enc;
     const sim_t* sim; const ldpc_code_t* code;
     float sigma; int point;
     /* shared accumulators */
@@ -64,9 +64,14 @@ static void* worker(void* arg)
         pthread_mutex_unlock(w->mu);
         uint64_t cnt[2];
         const double t0 = now_s();
-        int rc = ldpc_b200_awgn_device(w->h, w->d_llr, s->frames, w->sigma, s->seed + (uint64_t)w->point, first, NULL);
+        int rc;
+        if (s->real_encoder) {      /* random information bits -> systematic codeword -> BPSK + AWGN (ref: -encoder, main_p.cpp:232-233, GenericEncoder.cpp:38-78) */
+            rc = ldpc_b200_encode_device(w->enc, NULL, w->d_cw, s->frames, s->seed * 7919u + (uint64_t)w->point, first, NULL);
+            if (!rc) rc = ldpc_b200_awgn_codeword_device(w->h, w->d_llr, w->d_cw, s->frames, w->sigma, s->seed + (uint64_t)w->point, first, NULL);
+        } else rc = ldpc_b200_awgn_device(w->h, w->d_llr, s->frames, w->sigma, s->seed + (uint64_t)w->point, first, NULL);
         if (!rc) rc = ldpc_b200_decode_device(w->h, w->d_llr, w->d_hard, s->frames, s->iters, NULL, NULL);
-        if (!rc) rc = ldpc_b200_count_errors_device(w->h, w->d_hard, s->frames, cnt, NULL);
+        if (!rc) rc = s->real_encoder ? ldpc_b200_count_errors_ref_device(w->h, w->d_hard, w->d_cw, s->frames, cnt, NULL)
+                                      : ldpc_b200_count_errors_device(w->h, w->d_hard, s->frames, cnt, NULL);
         if (rc) { w->rc = rc; snprintf(w->err, sizeof(w->err), "%s", ldpc_b200_last_error(w->h)); *w->stop = 1; break; }
         w->decode_seconds += now_s() - t0; w->decoded += s->frames;
         pthread_mutex_lock(w->mu);
@@ -82,7 +87,7 @@ static int bits_range(const char* a) { int b = atoi(a); return (1 << (b - 1)) - 
 
 int main(int argc, char** argv)
 {
-    sim_t sim = { 0.5, 3.0, 0.1, 100, -1, 0, 0, 0, 0.0, 0.0, 30, 1, 65536, 0, 1 };             /* (ref: defaults main_p.cpp:118-122,134,142-143) */
+    sim_t sim = { 0.5, 3.0, 0.1, 100, -1, 0, 0, 0, 0.0, 0.0, 30, 1, 0, 65536, 0, 1 };             /* (ref: defaults main_p.cpp:118-122,134,142-143) */
     ldpc_params_t prm; ldpc_b200_default_params(&prm);
     const char *code_name = "576x288", *header = NULL, *table = NULL;
     int bits_llr = 6, bits_msg = 6, bits_var = 8, fraq = 3;                                     /* (ref: main_p.cpp:90-104) */
@@ -107,6 +112,7 @@ int main(int argc, char** argv)
         else if (!strcmp(a, "-timer")) { sim.timer_s = atoi(v); p++; }
         else if (!strcmp(a, "-qef")) { sim.ber_limit = 1; sim.ber_limit_value = atof(v); p++; }
         else if (!strcmp(a, "-tfer")) { sim.fer_limit = 1; sim.fer_limit_value = atof(v); p++; }
+        else if (!strcmp(a, "-encoder")) sim.real_encoder = 1;
         else if (!strcmp(a, "-bpsk") || !strcmp(a, "-Eb/N0") || !strcmp(a, "-random") || !strcmp(a, "-histo")) { /* accepted, no effect here */ }
         else if (!strcmp(a, "-thread")) { p++; /* host threads of the CPU simulator: the GPU build shards over -gpus instead */ }
         else if (!strcmp(a, "-sse")) prm.semantics = LDPC_SEM_X86_SSE;
@@ -194,8 +200,15 @@ int main(int argc, char** argv)
         if (ldpc_b200_device_alloc(w[g].h, &w[g].d_llr, sim.frames * (size_t)N * elem) || ldpc_b200_device_alloc(w[g].h, (void**)&w[g].d_hard, sim.frames * (size_t)N)) {
             printf("(EE) device allocation failed\n"); return 1;
         }
+        if (sim.real_encoder) {
+            if (sim.frames % 32) { printf("(EE) -encoder needs -frames to be a multiple of 32\n"); return 1; }
+            rc = ldpc_b200_encoder_create(&w[g].enc, &code, g);
+            if (rc) { printf("(EE) no systematic encoder for this table: %s\n", ldpc_b200_encoder_last_error(NULL)); return 1; }
+            if (ldpc_b200_device_alloc(w[g].h, (void**)&w[g].d_cw, sim.frames * (size_t)N)) { printf("(EE) device allocation failed\n"); return 1; }
+        }
     }
     int64_t kern = 0; ldpc_b200_get_info(w[0].h, LDPC_INFO_KERNEL, &kern);
+    printf("(II) ENCODER              : %s\n", sim.real_encoder ? "systematic, derived from H (random information bits)" : "all-zero codeword (CFakeEncoder)");
     printf("(II) DECODE KERNEL        : %s\n", kern == 2 ? "row-parallel, on-chip state" : kern == 3 ? "generic engine (fp32 arithmetic, HBM state)" : kern == 5 ? "generic engine (fp32 arithmetic, on-chip state)" : kern == 4 ? "frame-parallel, bulk-copy staged" : "frame-parallel, HBM state");
 
     const double t_simu = now_s();
@@ -246,7 +259,9 @@ int main(int argc, char** argv)
         if (sim.ber_limit && ber < sim.ber_limit_value) { printf("(II) THE SIMULATION HAS STOP DUE TO THE (USER) QUASI-ERROR FREE CONTRAINT (on BER).\n"); break; }
         if (sim.fer_limit && fer < sim.fer_limit_value) { printf("(II) THE SIMULATION HAS STOP DUE TO THE (USER) QUASI-ERROR FREE CONTRAINT (on FER).\n"); break; }
     }
-    for (int g = 0; g < sim.gpus; g++) { ldpc_b200_device_free(w[g].h, w[g].d_llr); ldpc_b200_device_free(w[g].h, w[g].d_hard); ldpc_b200_destroy(w[g].h); }
+    for (int g = 0; g < sim.gpus; g++) { ldpc_b200_device_free(w[g].h, w[g].d_llr); ldpc_b200_device_free(w[g].h, w[g].d_hard);
+        if (sim.real_encoder) { ldpc_b200_device_free(w[g].h, w[g].d_cw); ldpc_b200_encoder_destroy(w[g].enc); }
+        ldpc_b200_destroy(w[g].h); }
     ldpc_b200_free_code(&code);
     return 0;
 }

@@ -43,7 +43,11 @@ int ref_gpu_decode(int algo, const int8_t* llr, uint8_t* hard, int8_t* post, int
     CK(cudaMalloc((void**)&d_pos, sizeof(unsigned int) * _M));
     CK(cudaMemcpy(d_pos, PosNoeudsVariable, sizeof(unsigned int) * _M, cudaMemcpyHostToDevice));
     CK(cudaMalloc((void**)&d_msg, sizeof(unsigned int) * (size_t)_M * T));      /* d_MSG_C_2_V (ref: CGPUDecoder.cpp:36) */
-    CK(cudaMalloc((void**)&d_v, sizeof(unsigned int) * (size_t)_N * T));        /* device_V    (ref: CGPUDecoder.cpp:37) */
+    /* device_V (ref: CGPUDecoder.cpp:37), padded by 128 rows: InvInterleaver_uint8 reads whole 128-row chunks with its bounds check
+     * commented out (GPU_Transpose_uint8.cu:18,27-35) and discards what lies past _N only when writing (:48), so for _N % 128 != 0
+     * (576, 1200) it reads up to 64 rows beyond the array — harmless next to other allocations at the reference's small batch sizes,
+     * an illegal address at 64 Ki frames (seen here). */
+    CK(cudaMalloc((void**)&d_v, sizeof(unsigned int) * (size_t)(_N + 128) * T));
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     cudaEventRecord(e0);

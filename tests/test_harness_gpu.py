@@ -79,3 +79,12 @@ def test_c_simulator_float_flooding_and_code_header(built, tmp_path):
                    + "const unsigned short PosNoeudsVariable[_M] = {" + ", ".join(map(str, code.pos.tolist())) + "};\n")
     out, pts = run_sim("-fixed", "-gpu", "-OMS", 1, "-iter", 5, "-min", 2, "-max", 2, "-header", hdr, "-frames", 4096, "-max-frames", 4096)
     assert "(200,100)" in out and pts[2.0]["frames"] == 4096
+
+
+def test_c_simulator_real_encoder(built):
+    """-encoder: random codewords instead of the all-zero word; the FER point must sit where the all-zero one does"""
+    out, pts = run_sim("-fixed", "-avx", "-OMS", 1, "-iter", 10, "-min", 2, "-max", 2, "-fer", 1000, "-frames", 65536, "-max-frames", 65536, "-encoder")
+    out0, pts0 = run_sim("-fixed", "-avx", "-OMS", 1, "-iter", 10, "-min", 2, "-max", 2, "-fer", 1000, "-frames", 65536, "-max-frames", 65536)
+    assert "systematic, derived from H" in out and "all-zero codeword" in out0
+    fe, fe0 = pts[2.0]["fe"], pts0[2.0]["fe"]
+    assert 0.04 < pts[2.0]["fer"] < 0.062 and abs(fe - fe0) <= 4.0 * (fe + fe0) ** 0.5, (fe, fe0)
