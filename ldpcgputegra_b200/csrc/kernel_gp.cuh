@@ -69,20 +69,25 @@ template <> struct GpIO<int8_t> {
     static __device__ __forceinline__ void st(int8_t* p, float v) { *p = (int8_t)__float2int_rn(v); }
 };
 
+template <class S> struct GpIsFloat { static const bool value = false; };
+template <> struct GpIsFloat<float> { static const bool value = true; };
+
 __device__ __forceinline__ float gp_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // magnitude entering the min search (oracle/ldpc_oracle.c: magnitude())
+template <bool FLT>
 __device__ __forceinline__ float gp_magnitude(const GpMode& md, float x, int cls)
 {
-    if (md.is_float || md.sem == LDPC_SEM_GPU_FIXED) return fabsf(x);
+    if (FLT || md.sem == LDPC_SEM_GPU_FIXED) return fabsf(x);
     if (md.quirk && cls >= 1) return fabsf(fminf(x, md.sat_msg));
     return fminf(fabsf(x), md.sat_msg);
 }
 
 // the two magnitudes of a row (oracle/ldpc_oracle.c: row_constants())
+template <bool FLT>
 __device__ __forceinline__ void gp_constants(const GpMode& md, float min1, float min2, int cls, bool first, float& c1, float& c2)
 {
-    if (md.is_float) {
+    if (FLT) {
         if (md.algo == LDPC_ALGO_OMS) { c1 = fmaxf(__fsub_rn(min2, md.off), 0.0f); c2 = fmaxf(__fsub_rn(min1, md.off), 0.0f); }
         else { c1 = __fmul_rn(min2, md.f2); c2 = __fmul_rn(min1, md.f1); }
         return;
@@ -111,9 +116,16 @@ __device__ __forceinline__ void gp_constants(const GpMode& md, float min1, float
 // updated in place).
 // (state pointers, stride and mode are passed one by one, not as a struct: the on-chip engine calls this with shared-memory
 // pointers held in registers, and the mode must stay a kernel parameter in the constant bank)
-template <class S, int D, bool WRITE_V>
+// FLT = float mode (compile-time: float boundary type <=> float arithmetic without rails); IDX32 = the state fits 32-bit element
+// offsets (shared memory): the first profile of the on-chip engine spent 10 of 52 instructions per edge on 64-bit address math.
+template <bool IDX32> struct GpIdx { typedef size_t type; };
+template <> struct GpIdx<true> { typedef uint32_t type; };
+
+template <class S, int D, bool WRITE_V, bool FLT, bool IDX32>
 __device__ __forceinline__ void gp_row(const GpMode& md, S* V, S* MSG, const uint32_t* pos, int T, int t, size_t e, int cls, bool first)
 {
+    typedef typename GpIdx<IDX32>::type ix_t;
+    const bool x86 = !FLT && md.x86;
     float x[D], a[D];
     uint32_t idx[D];
     float min1 = md.min_init, min2 = md.min_init;
@@ -122,71 +134,73 @@ __device__ __forceinline__ void gp_row(const GpMode& md, S* V, S* MSG, const uin
     for (int j = 0; j < D; j++) idx[j] = __ldg(pos + e + j);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const float v = GpIO<S>::ld(V + (size_t)idx[j] * T + t);
-        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
+        const float v = GpIO<S>::ld(V + (ix_t)idx[j] * (ix_t)T + (ix_t)t);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (ix_t)(e + j) * (ix_t)T + (ix_t)t);
         float xx = __fsub_rn(v, m);
-        if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
+        if (!FLT) xx = gp_clamp(xx, md.lo, md.hi);
         x[j] = xx;
-        const float aa = gp_magnitude(md, xx, cls);
+        const float aa = gp_magnitude<FLT>(md, xx, cls);
         a[j] = aa;
         const float old = min1;
         min1 = fminf(min1, aa);
         min2 = fminf(min2, fmaxf(aa, old));
-        par ^= md.x86 ? (xx < 0.0f) : (xx > 0.0f);
+        par ^= x86 ? (xx < 0.0f) : (xx > 0.0f);
     }
     float c1, c2;
-    gp_constants(md, min1, min2, cls, first, c1, c2);
-    const int k = md.x86 ? (D & 1) : 1;       // negate = par ^ flag_j ^ k  (x86: degree parity; others: keep = par ^ pos_j)
+    gp_constants<FLT>(md, min1, min2, cls, first, c1, c2);
+    const int k = x86 ? (D & 1) : 1;       // negate = par ^ flag_j ^ k  (x86: degree parity; others: keep = par ^ pos_j)
 #pragma unroll
     for (int j = 0; j < D; j++) {
         const float mag = (a[j] == min1) ? c1 : c2;
-        const int flag = md.x86 ? (x[j] < 0.0f) : (x[j] > 0.0f);
+        const int flag = x86 ? (x[j] < 0.0f) : (x[j] > 0.0f);
         const float msg = (par ^ flag ^ k) ? -mag : mag;
-        GpIO<S>::st(MSG + (e + j) * T + t, msg);
+        GpIO<S>::st(MSG + (ix_t)(e + j) * (ix_t)T + (ix_t)t, msg);
         if (WRITE_V) {
             float vn = __fadd_rn(x[j], msg);
-            if (!md.is_float) vn = gp_clamp(vn, md.lo, md.hi);
-            GpIO<S>::st(V + (size_t)idx[j] * T + t, vn);
+            if (!FLT) vn = gp_clamp(vn, md.lo, md.hi);
+            GpIO<S>::st(V + (ix_t)idx[j] * (ix_t)T + (ix_t)t, vn);
         }
     }
 }
 
 // run-time degree (rows wider than 8: 2048x384 has degree 32, DVB-S2 rate 1/9 degree 27): two passes, the contributions are
 // recomputed from memory in the second one (L1/L2 hits) instead of being parked in local memory
-template <class S, bool WRITE_V>
+template <class S, bool WRITE_V, bool FLT, bool IDX32>
 __device__ __noinline__ void gp_row_rt(const GpMode& md, S* V, S* MSG, const uint32_t* pos, int T, int t, size_t e, int D, int cls, bool first)
 {
+    typedef typename GpIdx<IDX32>::type ix_t;
+    const bool x86 = !FLT && md.x86;
     float min1 = md.min_init, min2 = md.min_init;
     int par = 0;
 #pragma unroll 1
     for (int j = 0; j < D; j++) {
-        const float v = GpIO<S>::ld(V + (size_t)__ldg(pos + e + j) * T + t);
-        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
+        const float v = GpIO<S>::ld(V + (ix_t)__ldg(pos + e + j) * (ix_t)T + (ix_t)t);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (ix_t)(e + j) * (ix_t)T + (ix_t)t);
         float xx = __fsub_rn(v, m);
-        if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
-        const float aa = gp_magnitude(md, xx, cls);
+        if (!FLT) xx = gp_clamp(xx, md.lo, md.hi);
+        const float aa = gp_magnitude<FLT>(md, xx, cls);
         const float old = min1;
         min1 = fminf(min1, aa);
         min2 = fminf(min2, fmaxf(aa, old));
-        par ^= md.x86 ? (xx < 0.0f) : (xx > 0.0f);
+        par ^= x86 ? (xx < 0.0f) : (xx > 0.0f);
     }
     float c1, c2;
-    gp_constants(md, min1, min2, cls, first, c1, c2);
-    const int k = md.x86 ? (D & 1) : 1;
+    gp_constants<FLT>(md, min1, min2, cls, first, c1, c2);
+    const int k = x86 ? (D & 1) : 1;
 #pragma unroll 1
     for (int j = 0; j < D; j++) {
-        const size_t vi = (size_t)__ldg(pos + e + j) * T + t;
+        const size_t vi = (ix_t)__ldg(pos + e + j) * (ix_t)T + (ix_t)t;
         const float v = GpIO<S>::ld(V + vi);
-        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (e + j) * T + t);
+        const float m = first ? 0.0f : GpIO<S>::ld(MSG + (ix_t)(e + j) * (ix_t)T + (ix_t)t);
         float xx = __fsub_rn(v, m);
-        if (!md.is_float) xx = gp_clamp(xx, md.lo, md.hi);
-        const float mag = (gp_magnitude(md, xx, cls) == min1) ? c1 : c2;
-        const int flag = md.x86 ? (xx < 0.0f) : (xx > 0.0f);
+        if (!FLT) xx = gp_clamp(xx, md.lo, md.hi);
+        const float mag = (gp_magnitude<FLT>(md, xx, cls) == min1) ? c1 : c2;
+        const int flag = x86 ? (xx < 0.0f) : (xx > 0.0f);
         const float msg = (par ^ flag ^ k) ? -mag : mag;
-        GpIO<S>::st(MSG + (e + j) * T + t, msg);
+        GpIO<S>::st(MSG + (ix_t)(e + j) * (ix_t)T + (ix_t)t, msg);
         if (WRITE_V) {
             float vn = __fadd_rn(xx, msg);
-            if (!md.is_float) vn = gp_clamp(vn, md.lo, md.hi);
+            if (!FLT) vn = gp_clamp(vn, md.lo, md.hi);
             GpIO<S>::st(V + vi, vn);
         }
     }
@@ -198,11 +212,11 @@ __device__ __forceinline__ void gp_all_rows(const GpArgs<S>& A, int t, bool firs
     size_t e = 0;
     for (int c = 0; c < A.nb_deg; c++) {
         const int D = A.deg[c], R = A.rows[c];
-#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V>(A.md, A.V, A.MSG, A.pos, A.T, t, e, c, first); break;
+#define GP_CASE(DD) case DD: for (int r = 0; r < R; r++, e += DD) gp_row<S, DD, WRITE_V, GpIsFloat<S>::value, false>(A.md, A.V, A.MSG, A.pos, A.T, t, e, c, first); break;
         switch (D) {
             GP_CASE(3) GP_CASE(4) GP_CASE(5) GP_CASE(6) GP_CASE(7) GP_CASE(8)
         default:
-            for (int r = 0; r < R; r++, e += D) gp_row_rt<S, WRITE_V>(A.md, A.V, A.MSG, A.pos, A.T, t, e, D, c, first);
+            for (int r = 0; r < R; r++, e += D) gp_row_rt<S, WRITE_V, GpIsFloat<S>::value, false>(A.md, A.V, A.MSG, A.pos, A.T, t, e, D, c, first);
         }
 #undef GP_CASE
     }

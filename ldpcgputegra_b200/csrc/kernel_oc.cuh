@@ -38,16 +38,17 @@ struct OcArgs {
 };
 
 // flooding, variable-node half for one (variable, frame): clamp(llr + sum of the column's new messages), ascending edge order
+template <bool FLT>
 __device__ __forceinline__ void oc_vn_one(const GpMode& md, float* V, const float* MSG, const float* LLR, const int32_t* cptr, const int32_t* cedge, int F, int f, int n)
 {
     float s = LLR[n * F + f];
     const int k1 = __ldg(cptr + n + 1);
     for (int k = __ldg(cptr + n); k < k1; k++) s = __fadd_rn(s, MSG[__ldg(cedge + k) * F + f]);
-    if (!md.is_float) s = gp_clamp(s, md.lo, md.hi);
+    if (!FLT) s = gp_clamp(s, md.lo, md.hi);
     V[n * F + f] = s;
 }
 
-template <bool WRITE_V>
+template <bool WRITE_V, bool FLT>
 __device__ __forceinline__ void oc_level(const GpMode& md, float* V, float* MSG, const uint32_t* pos, const OcRow* rows, int r0, int nr, int F, const int* s_done, bool first)
 {
     const int tasks = nr * F;
@@ -55,10 +56,10 @@ __device__ __forceinline__ void oc_level(const GpMode& md, float* V, float* MSG,
         const int ri = t / F, f = t - ri * F;
         if (s_done[f]) continue;
         const OcRow row = rows[r0 + ri];
-#define OC_CASE(DD) case DD: gp_row<float, DD, WRITE_V>(md, V, MSG, pos, F, f, row.e0, row.cls, first); break;
+#define OC_CASE(DD) case DD: gp_row<float, DD, WRITE_V, FLT, true>(md, V, MSG, pos, F, f, row.e0, row.cls, first); break;
         switch (row.deg) {
             OC_CASE(3) OC_CASE(4) OC_CASE(5) OC_CASE(6) OC_CASE(7) OC_CASE(8)
-        default: gp_row_rt<float, WRITE_V>(md, V, MSG, pos, F, f, row.e0, row.deg, row.cls, first);
+        default: gp_row_rt<float, WRITE_V, FLT, true>(md, V, MSG, pos, F, f, row.e0, row.deg, row.cls, first);
         }
 #undef OC_CASE
     }
@@ -71,14 +72,14 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
     __shared__ int s_done[OC_MAXF], s_bad[OC_MAXF];
     const int F = A.F, n = A.n, m = A.m, tid = threadIdx.x;
     float* Vs = oc_smem; float* Ms = Vs + (size_t)n * F; float* Ls = Ms + (size_t)m * F;
-    const bool posterior_syndrome = A.md.is_float || A.flooding;
+    const bool posterior_syndrome = GpIsFloat<S>::value || A.flooding;
 
     for (size_t base = (size_t)blockIdx.x * F; base < A.frames; base += (size_t)gridDim.x * F) {
         const int valid = (int)min((size_t)F, A.frames - base);
         for (int i = tid; i < valid * n; i += (int)blockDim.x) {          // frame-major LLRs -> [n][F] fp32, clamped to the rails
             const int f = i / n, nn = i - f * n;
             float v = (float)A.llr[(base + f) * (size_t)n + nn];
-            if (!A.md.is_float) v = gp_clamp(v, A.md.lo, A.md.hi);
+            if (!GpIsFloat<S>::value) v = gp_clamp(v, A.md.lo, A.md.hi);
             Vs[(size_t)nn * F + f] = v;
             if (A.flooding) Ls[(size_t)nn * F + f] = v;
         }
@@ -90,14 +91,14 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
             const bool first = it == 0;
             for (int L = 0; L < A.nlevels; L++) {
                 const int r0 = __ldg(A.level_ptr + L), nr = __ldg(A.level_ptr + L + 1) - r0;
-                if (A.flooding) oc_level<false>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
-                else oc_level<true>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
+                if (A.flooding) oc_level<false, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
+                else oc_level<true, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
                 __syncthreads();
             }
             if (A.flooding) {
                 for (int t = tid; t < n * F; t += (int)blockDim.x) {
                     const int nn = t / F, f = t - nn * F;
-                    if (!s_done[f]) oc_vn_one(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn);
+                    if (!s_done[f]) oc_vn_one<GpIsFloat<S>::value>(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn);
                 }
                 __syncthreads();
             }
