@@ -108,3 +108,16 @@ def test_product_path_never_imports_the_oracle():
             text = p.read_text()
             for pat in (r'#include\s*[<"][^>"]*oracle', r'^\s*(from|import)\s+\S*(oracle|_helpers)', r'liboracle', r'oracle_decode', r'dlopen'):
                 assert not re.search(pat, text, flags=re.M), (p, pat)
+
+
+def test_encoder_analysis_runs_on_the_host(built):
+    """The encoder's table analysis (peeling order, GF(2) inverse) is host code and runs before any device is touched: tables whose
+    last n_checks columns are singular are refused as UNSUPPORTED with or without a GPU; good tables get as far as the device."""
+    with pytest.raises(pkg.LdpcError) as e:
+        pkg.Encoder(pkg.Code.load("2048x384"))
+    assert e.value.status == pkg.ERR_UNSUPPORTED and "singular" in str(e.value)
+    if pkg.lib().ldpc_b200_device_count() == 0:
+        for name in ("576x288", "64800x32400"):
+            with pytest.raises(pkg.LdpcError) as e:
+                pkg.Encoder(pkg.Code.load(name))
+            assert e.value.status == pkg.ERR_NO_DEVICE
