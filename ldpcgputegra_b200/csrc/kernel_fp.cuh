@@ -33,14 +33,15 @@ struct FpArgs {
 #define FP_BLOCK 128
 
 // ---- the arithmetic of one row on packed words: wv[j] = biased posteriors of 4 frames, wm[j] = messages + 128 -----------
-template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
+// G = frame pairs per word: 2 (four frames in 32 bits) or 1 (two frames in the low 16 bits; the staged kernel's small-batch variant)
+template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q, int G = 2>
 __device__ __forceinline__ void fp_row_math(const uint32_t (&wv)[D], const uint32_t (&wm)[D], const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi,
                                             uint32_t (&nv)[D], uint32_t (&nm)[D])
 {
     uint32_t ov[2][D], om[2][D];
     const h2 inv256 = h2_const(1.0f / 256.0f), half = h2_const(0.5f), m4 = h2_const(-4.0f);
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < G; g++) {
         h2 xu[D], a[D];
         uint32_t f[D];
 #pragma unroll
@@ -64,7 +65,8 @@ __device__ __forceinline__ void fp_row_math(const uint32_t (&wv)[D], const uint3
     }
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        nv[j] = pack_bytes(ov[0][j], ov[1][j]); nm[j] = pack_bytes(om[0][j], om[1][j]);
+        if (G == 2) { nv[j] = pack_bytes(ov[0][j], ov[1][j]); nm[j] = pack_bytes(om[0][j], om[1][j]); }
+        else { nv[j] = __byte_perm(ov[0][j], 0u, 0x4420); nm[j] = __byte_perm(om[0][j], 0u, 0x4420); }
         if (ET) {   // frozen frames keep their state
             const uint32_t keep = __byte_perm(keep_lo, keep_hi, 0x6420);
             nv[j] = (wv[j] & keep) | (nv[j] & ~keep);

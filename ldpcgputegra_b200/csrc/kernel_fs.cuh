@@ -25,9 +25,9 @@
 
 namespace ldpcb200 {
 
-#define FS_CONSUMERS 128                 // consumer threads per CTA (4 warps); +1 producer warp
-#define FS_THREADS (FS_CONSUMERS + 32)
-#define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line
+#define FS_CONSUMERS 128                 // granularity of the state arrays' row pitch (words); a CTA has NC = 128, 256 or 512 consumer threads + 1 producer warp
+#define FS_MAX_CONSUMERS 512
+#define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
 #define FS_MAXDEG 8
 #define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
 #define FS_FWD 4                         // rows whose outputs stay in the forwarding ring
@@ -43,6 +43,8 @@ struct FsArgs {
     int deg[LDPC_MAX_DEG_CLASSES];
     int rows[LDPC_MAX_DEG_CLASSES];
     int iters, stages, max_deg;
+    int nc;                  // consumer threads per CTA (128 | 256 | 512): a staged line is nc * 4 bytes.  The bulk-copy engine serves a
+                             // request in ~70 cycles whatever its size, so 512-byte lines cap the SM at ~7 B/clk (measured); wider CTAs lift that
     ldpc_params_t prm;
 };
 
@@ -67,10 +69,11 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // thread's own earlier stores
 // The stage of the PREVIOUS row is handed back here, between this row's arithmetic and its stores: the fence then only has
 // to cover stores that were issued a whole row ago, so it never waits on fresh ones.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q>
-__device__ __forceinline__ void fs_row(const FsArgs& A, int t, int tid, size_t e, uint32_t stage_s, const RowConsts& K, uint32_t prev_empty, int lane,
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC>
+__device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e, uint32_t stage_s, const RowConsts& K, uint32_t prev_empty, int lane,
                                        uint32_t fwd_s, uint32_t q, bool fwd_ok)
 {
+    constexpr uint32_t LINE = NC * 4u;
     uint32_t p2[D], wv[D], wm[D], nv[D], nm[D];
 #pragma unroll
     for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
@@ -79,12 +82,12 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int t, int tid, size_t e
         if (p2[j] & FS_F_HAZARD) {
             if ((p2[j] & FS_F_FWD) && fwd_ok) {
                 const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 25) & 7u;
-                wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * FS_CONSUMERS + tid) * 4u);
+                wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * NC + tid) * 4u);
             } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
-        } else wv[j] = lds_u32(stage_s + j * FS_LINE + 4 * tid);
+        } else wv[j] = lds_u32(stage_s + j * LINE + 4 * tid);
     }
 #pragma unroll
-    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * FS_LINE + 4 * tid);
+    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * LINE + 4 * tid);
     fp_row_math<SEM, ALGO, D, FIRST, false, Q>(wv, wm, K, 0u, 0u, nv, nm);
     fence_proxy_async_global();                    // the previous rows' stores, before any later bulk copy of the same lines
     __syncwarp();
@@ -93,29 +96,30 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int t, int tid, size_t e
     for (int j = 0; j < D; j++) {
         A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t] = nv[j];
         A.MSG[(e + j) * A.T + t] = nm[j];
-        sts_u32(fwd_s + (((q & (FS_FWD - 1)) * FS_MAXDEG + j) * FS_CONSUMERS + tid) * 4u, nv[j]);
+        sts_u32(fwd_s + (((q & (FS_FWD - 1)) * FS_MAXDEG + j) * NC + tid) * 4u, nv[j]);
     }
 }
 
-template <int SEM, int ALGO>
-__global__ void __launch_bounds__(FS_THREADS) fs_decode_kernel(const __grid_constant__ FsArgs A)
+template <int SEM, int ALGO, int NC>
+__global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
+    constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];
     // layout: full[K] | empty[K] | pad to 128 | forwarding ring | K stages of 2*max_deg lines
     const int Kst = A.stages;
     const uint32_t bars = smem_u32(fs_smem);
     const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
-    const uint32_t ring = fwd_s + FS_FWD * FS_MAXDEG * FS_LINE;
-    const uint32_t stage_bytes = (uint32_t)(2 * A.max_deg) * FS_LINE;
+    const uint32_t ring = fwd_s + FS_FWD * FS_MAXDEG * LINE;
+    const uint32_t stage_bytes = (uint32_t)(2 * A.max_deg) * LINE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * FS_CONSUMERS;
+    const int t0 = blockIdx.x * NC;
     if (threadIdx.x == 0) {
-        for (int k = 0; k < Kst; k++) { mbar_init(bars + 8 * k, 1); mbar_init(bars + 8 * (Kst + k), FS_CONSUMERS / 32); }
+        for (int k = 0; k < Kst; k++) { mbar_init(bars + 8 * k, 1); mbar_init(bars + 8 * (Kst + k), NC / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == FS_CONSUMERS / 32) {
+    if (warp == NC / 32) {
         // ---------------- producer warp: lanes 0-7 fetch the posterior lines, lanes 8-15 the message lines of one row ----------
         int stage = 0; uint32_t phase = 0;
         const int j = lane & 7;
@@ -131,10 +135,10 @@ __global__ void __launch_bounds__(FS_THREADS) fs_decode_kernel(const __grid_cons
                     const bool do_m = lane >= 8 && lane < 16 && j < D && it > 0;
                     const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, do_v || do_m));
                     const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
-                    if (lane == 0) mbar_arrive_expect_tx(full, n_lines * FS_LINE);
+                    if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
                     __syncwarp();
-                    if (do_v) bulk_g2s(dst0 + j * FS_LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), FS_LINE, full);
-                    if (do_m) bulk_g2s(dst0 + (A.max_deg + j) * FS_LINE, A.MSG + ((e + j) * A.T + t0), FS_LINE, full);
+                    if (do_v) bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
+                    if (do_m) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
                     if (++stage == Kst) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -159,8 +163,8 @@ __global__ void __launch_bounds__(FS_THREADS) fs_decode_kernel(const __grid_cons
                 const uint32_t st_s = ring + (uint32_t)stage * stage_bytes;
 #define FS_CASE(DD)                                                                                                   \
     case DD:                                                                                                          \
-        if (it == 0) { if (quirk) fs_row<SEM, ALGO, DD, true, true>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, true, false>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
-        else         { if (quirk) fs_row<SEM, ALGO, DD, false, true>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, false, false>(A, t, tid, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
+        if (it == 0) { if (quirk) fs_row<SEM, ALGO, DD, true, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, true, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
+        else         { if (quirk) fs_row<SEM, ALGO, DD, false, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, false, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
         break;
                 switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) }
 #undef FS_CASE

@@ -51,9 +51,12 @@ static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStre
 template <int SEM, int ALGO>
 static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    fs_decode_kernel<SEM, ALGO><<<blocks, FS_THREADS, smem, st>>>(a);
+#define FS_LAUNCH(NCV)                                                                                                                  \
+    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return (int)e;                                                                                                 \
+      fs_decode_kernel<SEM, ALGO, NCV><<<blocks, NCV + 32, smem, st>>>(a); }
+    if (a.nc == 512) FS_LAUNCH(512) else if (a.nc == 256) FS_LAUNCH(256) else FS_LAUNCH(128)
+#undef FS_LAUNCH
     return (int)cudaGetLastError();
 }
 #define LDPC_CASE(FN, SEM, ALGO, ...) return et ? FN<SEM, ALGO, true>(__VA_ARGS__) : FN<SEM, ALGO, false>(__VA_ARGS__)

@@ -409,8 +409,10 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         return LDPC_OK;
     }
     // frame-parallel: interleave -> decode -> de-interleave + hard decision
-    const int tq = h->kernel == 4 ? FS_CONSUMERS : 32;
-    const int T = (int)(((frames + 3) / 4 + tq - 1) / tq * tq);
+    const size_t t4 = (frames + 3) / 4;
+    const int knob = h->prm.reserved[3];
+    const int tq = h->kernel != 4 ? 32 : (knob == 128 || knob == 256 || knob == 512) ? knob : FS_CONSUMERS;
+    const int T = (int)((t4 + tq - 1) / tq * tq);
     int rc;
     if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
     if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
@@ -432,14 +434,20 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         f.V = s.d_V; f.MSG = s.d_MSG; f.pos2 = h->d_pos2; f.T = T; f.n = c.n; f.m = c.m; f.nb_deg = c.nb_deg;
         for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { f.deg[i] = c.deg[i]; f.rows[i] = c.rows[i]; }
         f.iters = iters; f.max_deg = h->fs_max_deg; f.prm = h->prm;
+        // consumers per CTA: 128.  Wider CTAs (256 / 512 consumers = 1 KB / 2 KB lines, a quarter of the bulk-copy requests) were built to
+        // test whether the copy engine's request rate bounds the kernel: it does not (DVB-S2, 256 Ki frames: 570 / 576 / 583 ms for
+        // 128 / 256 / 512) — the consumers' issue slots do (profiles/r01_ncu_fs_v2.txt: 66 % issue-active, 636 warp instructions per row).
+        int nc = 128;
+        if (h->prm.reserved[3] == 128 || h->prm.reserved[3] == 256 || h->prm.reserved[3] == 512) { if (T % h->prm.reserved[3] == 0) nc = h->prm.reserved[3]; }   // experiment knob
+        f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
-        const int ctas = T / FS_CONSUMERS, per_sm = std::min(4, (ctas + h->sms - 1) / h->sms);
-        const size_t stage_bytes = (size_t)2 * f.max_deg * FS_LINE;
-        int stages = (int)(((size_t)(220 * 1024) / per_sm - (size_t)FS_FWD * FS_MAXDEG * FS_LINE - 256) / stage_bytes);
+        const int ctas = T / nc, per_sm = std::min(4, (ctas + h->sms - 1) / h->sms);
+        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)2 * f.max_deg * line, fwd_bytes = (size_t)FS_FWD * FS_MAXDEG * line;
+        int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if (h->prm.reserved[4] >= 2 && h->prm.reserved[4] < FS_HAZARD) stages = h->prm.reserved[4];     // experiment knob
         f.stages = stages;
-        const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + (size_t)FS_FWD * FS_MAXDEG * FS_LINE + stages * stage_bytes;
+        const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + fwd_bytes + stages * stage_bytes;
         fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fs_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fs_uniform
                         : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fs_arm : launch_fs_gpu;
         if (iters > 0) CU_TRY(h, (cudaError_t)fn(h->prm.algo, f, ctas, smem, st));
@@ -725,7 +733,7 @@ int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* ha
     if (iters_done) {
         if (h->kernel == 2 || h->kernel == 5) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
         else if (h->kernel == 3) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (frames + 31) / 32 * 32))) return rc; d_it = s.d_iters; }
-        else { const size_t tq = h->kernel == 4 ? FS_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
+        else { const size_t tq = h->kernel == 4 ? FS_MAX_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
     }
     CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n * el, cudaMemcpyHostToDevice, s.stream));
     const bool dbg = h->debug && slot == 0;
