@@ -9,7 +9,9 @@
 // They compile against the C ABI only (no CUDA headers needed).  Error behaviour mirrors the reference: print and exit(0)
 // (ref: code/gpu_fixed/custom_api/custom_cuda.cu:5-17, CGPU_Decoder_OMS_SIMD.cu:101-105).  When included from inside the
 // reference tree define LDPC_B200_DERIVE_FROM_REFERENCE before including, after the reference's own class header, and the
-// adapters derive from CGPUDecoder / CDecoder_fixed so they fit the reference's factory and pointer types.
+// adapters derive from CGPUDecoder / CDecoder_fixed so they fit the reference's factory and pointer types.  Each adapter derives
+// only when its own base class has been declared (the two harness trees never include both): the reference headers' include
+// guards tell (__CLASS_CGPUDecoder__, code/gpu_fixed/decoder_template/CGPUDecoder.h:14; __CDecoder_fixed__, code/x86/CDecoder/template/CDecoder_fixed.h).
 #ifndef CGPU_DECODER_B200_H
 #define CGPU_DECODER_B200_H
 
@@ -59,15 +61,22 @@ inline ldpc_code_t code_from_reference_macros(const IndexT* table, uint32_t* sto
 // call moves 4*nb_frames frames: var_nodes really holds int8 [4*nb_frames][n], Rprime_fix receives bytes in {0,1}
 // (ref: CGPU_Decoder_OMS_SIMD.cu:111,146).
 // ---------------------------------------------------------------------------------------------------------------------
+#if defined(LDPC_B200_DERIVE_FROM_REFERENCE) && defined(__CLASS_CGPUDecoder__)
+#define LDPC_B200_DERIVE_GPU 1
+#endif
+#if defined(LDPC_B200_DERIVE_FROM_REFERENCE) && (defined(__CDecoder_fixed__) || defined(LDPC_B200_HAVE_CDECODER_FIXED))
+#define LDPC_B200_DERIVE_X86 1
+#endif
+
 class CGPU_Decoder_B200
-#ifdef LDPC_B200_DERIVE_FROM_REFERENCE
+#ifdef LDPC_B200_DERIVE_GPU
     : public CGPUDecoder
 #endif
 {
 public:
     // algo: "MS" | "OMS" | "NMS" | "2NMS" — the reference picks the subclass from argv (code/gpu_fixed/test.cpp:241-276)
     CGPU_Decoder_B200(size_t _nb_frames, size_t n, size_t k, size_t m, const ldpc_code_t& code, const char* algo = "OMS", int device = 0)
-#ifdef LDPC_B200_DERIVE_FROM_REFERENCE
+#ifdef LDPC_B200_DERIVE_GPU
         : CGPUDecoder(0, n, k, m)
 #endif
     {
@@ -110,7 +119,7 @@ private:
 // first decode so that the setters behave like the reference's.
 // ---------------------------------------------------------------------------------------------------------------------
 class CDecoder_B200
-#ifdef LDPC_B200_DERIVE_FROM_REFERENCE
+#ifdef LDPC_B200_DERIVE_X86
     : public CDecoder_fixed
 #endif
 {
