@@ -135,12 +135,17 @@ __device__ __noinline__ void rp_row_generic(uint32_t ub, uint32_t msa, uint32_t 
     }
 }
 
-// specialised variants: id = 1 + (deg - 6) * 2 + (stride == 32)  for deg in {6,7,8}, stride in {24,32}
+// specialised variants: id = 1 + (deg - 6) * 5 + stride index, for deg in {6,7,8}, stride in {24,32,64,96,128}
 __host__ __device__ __forceinline__ int rp_variant_id(int deg, int stride)
 {
-    if (deg < 6 || deg > 8 || (stride != 24 && stride != 32)) return 0;
-    return 1 + (deg - 6) * 2 + (stride == 32 ? 1 : 0);
+    const int si = stride == 24 ? 0 : stride == 32 ? 1 : stride == 64 ? 2 : stride == 96 ? 3 : stride == 128 ? 4 : -1;
+    if (deg < 6 || deg > 8 || si < 0) return 0;
+    return 1 + (deg - 6) * 5 + si;
 }
+#define RP_ALL_CASES                                                                                  \
+    RP_CASE(1, 6, 24) RP_CASE(2, 6, 32) RP_CASE(3, 6, 64) RP_CASE(4, 6, 96) RP_CASE(5, 6, 128)        \
+    RP_CASE(6, 7, 24) RP_CASE(7, 7, 32) RP_CASE(8, 7, 64) RP_CASE(9, 7, 96) RP_CASE(10, 7, 128)       \
+    RP_CASE(11, 8, 24) RP_CASE(12, 8, 32) RP_CASE(13, 8, 64) RP_CASE(14, 8, 96) RP_CASE(15, 8, 128)
 
 // everything the step loop needs, in registers: shared-window addresses and group geometry
 struct RpCtx {
@@ -249,7 +254,7 @@ __device__ __forceinline__ void rp_dispatch_static(const RpCtx& c, const RpRun& 
 {
 #define RP_CASE(ID, DD, NN) case ID: rp_run_static<SEM, ALGO, DD, NN, FIRST, ET, Q>(c, r, L, K); break;
     switch (r.variant) {
-        RP_CASE(1, 6, 24) RP_CASE(2, 6, 32) RP_CASE(3, 7, 24) RP_CASE(4, 7, 32) RP_CASE(5, 8, 24) RP_CASE(6, 8, 32)
+        RP_ALL_CASES
     }
 #undef RP_CASE
 }
@@ -271,7 +276,7 @@ __device__ __forceinline__ void rp_dispatch(const RpCtx& c, const RpRun& r, int 
 {
 #define RP_CASE(ID, DD, NN) case ID: rp_run<SEM, ALGO, DD, NN, FIRST, ET, Q>(c, r.first, r.count, valid_pairs, K); break;
     switch (r.variant) {
-        RP_CASE(1, 6, 24) RP_CASE(2, 6, 32) RP_CASE(3, 7, 24) RP_CASE(4, 7, 32) RP_CASE(5, 8, 24) RP_CASE(6, 8, 32)
+        RP_ALL_CASES
     default: rp_run<SEM, ALGO, 0, 0, FIRST, ET, Q>(c, r.first, r.count, valid_pairs, K);
     }
 #undef RP_CASE

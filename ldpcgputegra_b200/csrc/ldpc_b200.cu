@@ -176,13 +176,32 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     struct Tmp { RpStep st; std::vector<int> rows; };
     std::vector<Tmp> tmp;
     int off = 0;
+    // Step size.  Normally a (level, degree class) group of rows is cut into steps of <= 32 rows.  When every group of the code
+    // is a multiple of one size S in (32, 128] (QC codes with a large circulant: 2304x1152 -> 96, 1944x972 -> 81, 1248x624 -> 52),
+    // steps of S rows let ONE frame pair occupy 2-4 warps, which is where such codes get their parallelism from: only a handful of
+    // their pairs fit in shared memory (2304x1152: 5 per SM = 5 warps with 32-row steps, 15 with 96-row steps).
+    int big_step = 0;
+    if (h->prm.reserved[3] != 3) {       // reserved[3] == 3: force the 32-row steps (A/B experiments)
+        int g = 0;
+        for (int L = 0; L < levels; L++)
+            for (int k = 0; k < c.nb_deg; k++) {
+                int cnt = 0;
+                for (int r : by_level[L]) cnt += row_cls[r] == k;
+                if (cnt) { int a = g, b = cnt; while (b) { const int t_ = a % b; a = b; b = t_; } g = a; }
+            }
+        int S = g;
+        for (int d = 2; S > 128 && d <= g; d++) if (g % d == 0 && g / d <= 128) S = g / d;
+        bool degs_ok = true;
+        for (int k = 0; k < c.nb_deg; k++) degs_ok = degs_ok && c.deg[k] >= 6 && c.deg[k] <= 8;     // the strides 64/96/128 exist as specialised variants only
+        if (S > 32 && S <= 128 && degs_ok) big_step = S;
+    }
     for (int L = 0; L < levels; L++) {
         bool first = true;
         for (int k = 0; k < c.nb_deg; k++) {
             std::vector<int> rows;
             for (int r : by_level[L]) if (row_cls[r] == k) rows.push_back(r);
             if (rows.empty()) continue;
-            const int rounds = ((int)rows.size() + 31) / 32;
+            const int rounds = big_step ? (int)rows.size() / big_step : ((int)rows.size() + 31) / 32;
             const int per = ((int)rows.size() + rounds - 1) / rounds;
             for (int q = 0; q < rounds; q++) {
                 const int b = q * per, e = std::min((int)rows.size(), b + per);
@@ -190,9 +209,9 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
                 Tmp t; RpStep& st = t.st; memset(&st, 0, sizeof(st));
                 st.deg = (uint16_t)c.deg[k]; st.cls = (uint8_t)k; st.nrows = (uint16_t)(e - b); st.sync = first ? 1 : 0;
                 first = false;
-                // specialised instantiations exist for degree 6..8 with an element stride of 24 or 32 (immediate addressing)
+                // specialised instantiations exist for degree 6..8 with an element stride of 24, 32, 64, 96 or 128 (immediate addressing)
                 int stride = st.nrows;
-                if (st.deg >= 6 && st.deg <= 8 && st.nrows > 16) stride = st.nrows <= 24 ? 24 : 32;
+                if (st.deg >= 6 && st.deg <= 8 && st.nrows > 16) stride = st.nrows <= 24 ? 24 : (st.nrows + 31) / 32 * 32;
                 st.stride = (uint16_t)stride;
                 st.variant = (uint32_t)rp_variant_id(st.deg, stride);
                 st.msg_off = (uint32_t)off;
@@ -275,7 +294,7 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     // static plan: uniform steps, every run specialised, at most one task per lane of a full group
     bool all_special = true;
     for (auto& r : plan.runs) all_special = all_special && r.variant != 0;
-    plan.static_nrows = (uniform && all_special && plan.P * nr0 <= 32 * plan.G && h->prm.reserved[3] == 0) ? nr0 : 0;
+    plan.static_nrows = (uniform && all_special && plan.P * nr0 <= 32 * plan.G && h->prm.reserved[3] != 1) ? nr0 : 0;
     if (plan.static_nrows) {   // the static kernel is compiled for at most RP_STATIC_THREADS threads
         const int max_groups = RP_STATIC_THREADS / (32 * plan.G);
         if (max_groups < 1) plan.static_nrows = 0;
@@ -599,11 +618,14 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         const size_t pair_bytes = (size_t)h->rp_pair_words * 4;
         auto fixed_bytes = [&](int slots_) { return plan.steps.size() * sizeof(RpStep) + plan.runs.size() * sizeof(RpRun) + (((size_t)plan.m_elems * 2 + 15) / 16) * 16 + (((size_t)slots_ * 8 + 15) / 16) * 16; };
         const int slots = plan.slots;
-        // measured (profiles/r01_sweep_v5.jsonl): with >= 4 pairs per SM the on-chip kernel wins at every batch size (2304x1152,
-        // 5 pairs: 14.0 M frames/s against 4.2 for the frame-parallel kernel at 64 Ki frames); with 2-3 pairs (4000x2000) it wins
-        // for small batches (2.3 vs 0.6 M frames/s at 16 Ki) but the frame-parallel kernel overtakes it once the batch fills the
-        // GPU with threads (4.0 M frames/s at 128 Ki)
-        const int min_slots = params->kernel == 2 ? 1 : (h->max_frames >= 98304 ? 4 : 2);
+        // On-chip or frame-parallel?  The on-chip kernel lives on (pairs per SM) x (rows per level) concurrent row tasks: 576x288
+        // 23 x 29, 2304x1152 5 x 115, 200x100 71 x 6 all run 25-100 M frames/s; 1200x600 (464 levels: 8 x 1.3) or 816x408 (11 x 6.4)
+        // leave most lanes idle and the frame-parallel kernels win by 10-25x once the batch gives them threads
+        // (profiles/r01_sweep_v5.jsonl, r01_paper_codes.jsonl).  Small batches starve the frame-parallel kernels instead
+        // (4000x2000, 16 Ki frames: 2.3 M frames/s on chip, 0.6 M frame-parallel), so there the on-chip kernel is kept whenever it fits.
+        const double tasks_per_sm = (double)plan.slots * code->n_checks / std::max(1, h->levels);
+        const bool enough_tasks = tasks_per_sm >= 256.0 || h->max_frames < 32768;
+        const int min_slots = params->kernel == 2 ? 1 : (enough_tasks ? 2 : (1 << 30));
         if (slots >= min_slots) {
             h->kernel = 2; h->rp_G = plan.G; h->rp_P = plan.P; h->rp_slots = slots; h->rp_groups = (slots + plan.P - 1) / plan.P;
             h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size(); h->rp_static = plan.static_nrows;
