@@ -215,6 +215,9 @@ def default_params(**kw) -> ParamsT:
         if k == "fs_stages":      # ring depth of the staged frame-parallel kernel (A/B experiments)
             p.reserved[4] = int(v)
             continue
+        if k == "no_pair_fastest":   # keep lane -> (pair t / nrows, row t % nrows) in the static plan (A/B experiments)
+            p.reserved[3] = 5 if v else 0
+            continue
         if k == "small_steps":    # keep the <= 32-row steps of the on-chip plan even when the code allows 64-128-row steps (A/B experiments)
             p.reserved[3] = 3 if v else 0
             continue

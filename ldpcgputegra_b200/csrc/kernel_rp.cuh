@@ -61,6 +61,8 @@ struct RpArgs {
     int m_elems;              // padded message elements per pair (multiple of 4)
     int G, P;                 // warps per group, pairs per full group
     int static_nrows;         // > 0: every step has this many rows and P * nrows <= 32 * G — lane t owns (pair t / nrows, row t % nrows) for the whole decode
+    int pair_fastest;         // static plan, P = 4, pair pitch = 8 or 24 (mod 32 words): lane t owns (pair t % 4, row t / 4) instead — a warp is then
+                              // 8 rows x 4 pairs whose four 8-bank windows tile the 32 banks: posterior gathers and message accesses conflict-free
     int groups;               // groups per CTA
     int slots;                // pair slots per CTA (the last group may own fewer than P)
     int iters;
@@ -181,7 +183,7 @@ __device__ __forceinline__ void rp_run(const RpCtx& c, int first, int count, int
 // 4 pairs x 24 rows on 3 warps): a lane keeps its (pair, row slot) for the whole decode, so a step costs nothing but the
 // row itself — no descriptor load, no task -> (pair, row) arithmetic, addresses advance by a compile-time constant.
 // (profiles/r01_ncu_rp_v3_g34.txt: 32.9 warp instructions per warp-edge-update against ~22 in the row body.)
-struct RpLane { uint32_t ub, ms_lane, ix_lane, keep; bool active; };
+struct RpLane { uint32_t ub, ms_lane, ix_lane, keep, pair; bool active; };
 
 // row body with the addresses and the old messages already in registers (software-pipelined caller)
 template <int SEM, int ALGO, int D, int NR, bool FIRST, bool ET, bool Q>
@@ -464,8 +466,10 @@ __global__ void __launch_bounds__(STAT ? RP_STATIC_THREADS : RP_MAX_THREADS, 1) 
         RpLane L;                                          // static plan: this lane's (pair, row slot) for the whole decode
         const bool stat = STAT;
         {
-            const uint32_t lp = stat ? (uint32_t)c.gl / (uint32_t)A.static_nrows : 0u, lz = (uint32_t)c.gl - lp * (uint32_t)A.static_nrows;
-            L.active = stat && (int)lp < valid;
+            uint32_t lp = stat ? (uint32_t)c.gl / (uint32_t)A.static_nrows : 0u, lz = (uint32_t)c.gl - lp * (uint32_t)A.static_nrows;
+            if (stat && A.pair_fastest) { lp = (uint32_t)c.gl & 3u; lz = (uint32_t)c.gl >> 2; }
+            L.active = stat && (int)lp < valid && lz < (uint32_t)A.static_nrows;
+            L.pair = lp;
             L.ub = c.state_s + lp * c.pair_bytes; L.ms_lane = L.ub + c.ms_off + 4u * lz; L.ix_lane = c.idx_s + 2u * lz; L.keep = 0u;
         }
         const uint32_t runs_s = smem_u32(runs);
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(STAT ? RP_STATIC_THREADS : RP_MAX_THREADS, 1) 
                     group_sync(c.G, c.bar);
                     if (c.gl < valid) gflags[2 * c.gl] = 0u;       // cleared for the next syndrome pass (ordered by the barriers of the iteration)
                     if (!running) break;
-                    if (stat && L.active) L.keep = lds_u32(c.flags_s + 8u * ((uint32_t)c.gl / (uint32_t)A.static_nrows) + 4u);
+                    if (stat && L.active) L.keep = lds_u32(c.flags_s + 8u * L.pair + 4u);
                 }
                 if (stat) rp_iteration_static<SEM, ALGO, false, ET>(c, runs_s, A.nruns, L, K);
                 else rp_iteration<SEM, ALGO, false, ET>(c, runs, A.nruns, valid, K);

@@ -54,7 +54,7 @@ struct ldpc_b200_handle_s {
     OcRow* d_oc_rows = nullptr; int32_t* d_oc_levels = nullptr; int oc_nlevels = 0, oc_F = 0, oc_threads = 0; size_t oc_smem = 0;   // on-chip generic engine (kernel 5)
     int levels = 0, sms = 0;
     // row-parallel plan
-    int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0; size_t rp_smem = 0;
+    int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0, rp_pair_fastest = 0; size_t rp_smem = 0;
     RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
     uint32_t* d_pos2 = nullptr; int fs_max_deg = 0;    // staged frame-parallel kernel: edge table with hazard flags
@@ -158,7 +158,7 @@ GpMode make_gp_mode(const ldpc_params_t& p)
 // Build the row-parallel plan: levels -> steps of <= 32 same-degree rows, step-transposed index table, (G, P) grouping.
 struct RpPlan {
     std::vector<RpStep> steps; std::vector<RpRun> runs; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of;
-    int G = 1, P = 1, m_elems = 0, pair_pad = 0, slots = 0, static_nrows = 0;
+    int G = 1, P = 1, m_elems = 0, pair_pad = 0, slots = 0, static_nrows = 0, pair_fastest = 0; bool pair_pad_ok = false;
 };
 
 int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
@@ -290,11 +290,16 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     // experiment knob (not part of the reference's parameter set): reserved[0]/[1] force the grouping
     if (h->prm.reserved[0] > 0 && h->prm.reserved[0] <= 4 && h->prm.reserved[1] > 0 && h->prm.reserved[1] <= 8) { plan.G = h->prm.reserved[0]; plan.P = h->prm.reserved[1]; }
     plan.pair_pad = pad_for(plan.P);
+    plan.pair_pad_ok = plan.P > 1 && uniform && nr0 % 4 == 0;       // pad_for() really produced pitch = nrows (mod 32)
     plan.slots = slots_for(plan.G, plan.P, plan.pair_pad);
     // static plan: uniform steps, every run specialised, at most one task per lane of a full group
     bool all_special = true;
     for (auto& r : plan.runs) all_special = all_special && r.variant != 0;
     plan.static_nrows = (uniform && all_special && plan.P * nr0 <= 32 * plan.G && h->prm.reserved[3] != 1) ? nr0 : 0;
+    // lane -> (pair, row) with the pair index fastest when that makes a warp's four 8-row windows tile the 32 banks (pair pitch
+    // = nrows (mod 32) by pad_for(): 24 -> offsets 0/24/16/8, 8 -> 0/8/16/24); profiles/r01_ncu_rp_v6.txt had 23 % extra wavefronts
+    if (plan.static_nrows && plan.P == 4 && plan.pair_pad_ok && (nr0 % 32 == 24 || nr0 % 32 == 8) && 4 * nr0 == 32 * plan.G && h->prm.reserved[3] != 5)
+        plan.pair_fastest = 1;
     if (plan.static_nrows) {   // the static kernel is compiled for at most RP_STATIC_THREADS threads
         const int max_groups = RP_STATIC_THREADS / (32 * plan.G);
         if (max_groups < 1) plan.static_nrows = 0;
@@ -416,7 +421,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         a.idx_t = h->d_idx_t; a.edge_of = h->d_edge_of; a.steps = h->d_steps;
         a.runs = h->d_runs; a.nruns = h->rp_nruns; a.pair_words = h->rp_pair_words;
         a.frames = frames; a.n = c.n; a.m = c.m; a.nsteps = h->rp_nsteps; a.n_pad = h->rp_npad; a.m_elems = h->rp_melems;
-        a.static_nrows = h->rp_static;
+        a.static_nrows = h->rp_static; a.pair_fastest = h->rp_pair_fastest;
         a.G = h->rp_G; a.P = h->rp_P; a.groups = h->rp_groups; a.slots = h->rp_slots; a.iters = iters;
         a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.prm = h->prm;
         const size_t pairs = (frames + 1) / 2;
@@ -628,7 +633,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         const int min_slots = params->kernel == 2 ? 1 : (enough_tasks ? 2 : (1 << 30));
         if (slots >= min_slots) {
             h->kernel = 2; h->rp_G = plan.G; h->rp_P = plan.P; h->rp_slots = slots; h->rp_groups = (slots + plan.P - 1) / plan.P;
-            h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size(); h->rp_static = plan.static_nrows;
+            h->rp_nsteps = (int)plan.steps.size(); h->rp_nruns = (int)plan.runs.size(); h->rp_static = plan.static_nrows; h->rp_pair_fastest = plan.pair_fastest;
             h->rp_smem = fixed_bytes(slots) + pair_bytes * slots;
             CREATE_TRY(cudaMalloc((void**)&h->d_runs, plan.runs.size() * sizeof(RpRun)));
             CREATE_TRY(cudaMemcpy(h->d_runs, plan.runs.data(), plan.runs.size() * sizeof(RpRun), cudaMemcpyHostToDevice));
