@@ -133,3 +133,29 @@ def test_unsupported_combinations_fail_loudly(code576):
                dict(schedule="FLOODING", kernel=1), dict(dtype="I16", semantics="UNIFORM", sat_var=40000)]:
         with pytest.raises(pkg.LdpcError):
             pkg.CGPUDecoder(code576, nb_frames=64, device=0, **kw)
+
+
+def test_float_flooding_full_batch_properties(code576):
+    """BASELINE configs[2] at a full 65 536-frame batch (the on-chip generic engine picked by the library): strided sample against
+    the CPU restatement (decisions and iteration counts), frames independent (permutation equivariance), early termination only
+    ever stops frames whose syndrome is zero, FER where the fixed-point decoder puts it."""
+    F = 65536
+    dec = pkg.CGPUDecoder(code576, nb_frames=F, device=0, dtype="F32", algo="NMS", factor1=0.75, schedule="FLOODING", early_term=1)
+    assert dec.info(pkg.INFO_KERNEL) == 5
+    y = dec.awgn(F, pkg.sigma_for(2.5, 0.5), seed=2025)
+    hard, it = dec.decode(y, 40, want_iters=True)
+    sample = np.arange(0, F, 131)
+    o = oracle_decode_float(code576, dec.params, y[sample], 40)
+    assert np.array_equal(hard[sample], o["hard"]) and np.array_equal(it[sample], o["iters"])
+    perm = np.random.default_rng(2).permutation(F)
+    hard_p, it_p = dec.decode(y[perm], 40, want_iters=True)
+    assert np.array_equal(hard_p, hard[perm]) and np.array_equal(it_p, it[perm])
+    stopped = it < 40
+    e = r = 0; synd = np.zeros(F, bool)                       # H c for every frame
+    for d, cnt in zip(code576.deg, code576.rows):
+        idx = code576.pos[e:e + d * cnt].reshape(cnt, d).astype(np.int64)
+        synd |= ((hard[:, idx].sum(axis=2) & 1) != 0).any(axis=1)
+        e += d * cnt
+    assert stopped.mean() > 0.95 and not synd[stopped].any()
+    assert hard[:, :code576.k_info].any(axis=1).mean() < 0.02
+    dec.close()

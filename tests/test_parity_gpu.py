@@ -274,3 +274,23 @@ def test_reference_gpu_kernels(built, name):
     o1 = oracle_decode(c, g1["prm"], llr, 1)
     for k in ("hard", "post", "msgs"):
         assert np.array_equal(r1[k], g1[k]) and np.array_equal(r1[k], o1[k]), f"{name} 2NMS I1 {k}"
+
+
+def test_dvbs2_full_batch_properties(built):
+    """BASELINE configs[4] on a batch that fills the GPU's frame-parallel kernel (16 384 frames of 64 800 bits, 4.8 GB of state):
+    strided sample against the oracle, staged kernel == plain kernel on every frame, frames independent."""
+    c = Code.load("64800x32400")
+    F = 16384
+    dec = pkg.CGPUDecoder(c, nb_frames=F)
+    assert dec.info(pkg.INFO_KERNEL) == 4
+    llr = dec.awgn(F, pkg.sigma_for(1.0, 0.5), seed=31)
+    hard = dec.decode(llr, 10)
+    sample = np.arange(0, F, 1489)
+    assert np.array_equal(hard[sample], oracle_decode(c, dec.params, llr[sample], 10, want_state=False)["hard"])
+    d1 = pkg.CGPUDecoder(c, nb_frames=F, kernel=1)
+    assert np.array_equal(d1.decode(llr, 10), hard)
+    d1.close()
+    perm = np.random.default_rng(3).permutation(F)
+    assert np.array_equal(dec.decode(llr[perm], 10), hard[perm])
+    assert 0.0 < hard[:, :c.k_info].any(axis=1).mean() < 0.9       # 1 dB: the waterfall of this code, both outcomes present
+    dec.close()
