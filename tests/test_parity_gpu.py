@@ -294,3 +294,32 @@ def test_dvbs2_full_batch_properties(built):
     assert np.array_equal(dec.decode(llr[perm], 10), hard[perm])
     assert hard.any()                                               # 1 dB is below this code's waterfall at 10 iterations: real work, not all-zero output
     dec.close()
+
+
+def test_four_decoder_objects_on_four_host_threads(code576):
+    """The reference harness runs 4 decoder objects in 4 OpenMP sections against one GPU (code/gpu_fixed/test.cpp:241-281,347-393):
+    one handle per host thread, no shared mutable state.  Four threads decode different batches at once, several times over, with
+    different configurations; every result must equal the single-threaded one."""
+    import threading
+    cfgs = [dict(algo="OMS", semantics="X86_SSE"), dict(algo="NMS", semantics="GPU_FIXED"), dict(algo="OMS", semantics="ARM_SCALAR", early_term=1),
+            dict(algo="OMS", semantics="UNIFORM", kernel=4)]
+    batches = [awgn_llr(code576, 3000 + 17 * i, 1.0 + 0.5 * i, 400 + i) for i in range(4)]
+    expect = []
+    for kw, llr in zip(cfgs, batches):
+        d = pkg.CGPUDecoder(code576, nb_frames=llr.shape[0], device=0, **kw); expect.append(d.decode(llr, 8)); d.close()
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            d = pkg.CGPUDecoder(code576, nb_frames=batches[i].shape[0], device=0, **cfgs[i])
+            for _ in range(5):
+                results[i] = d.decode(batches[i], 8)
+            d.close()
+        except Exception as e:      # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errors, errors
+    for i in range(4):
+        assert np.array_equal(results[i], expect[i]), f"thread {i} ({cfgs[i]})"
