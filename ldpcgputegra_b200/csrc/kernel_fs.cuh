@@ -28,12 +28,12 @@ namespace ldpcb200 {
 #define FS_CONSUMERS 128                 // granularity of the state arrays' row pitch (words); a CTA has NC = 128, 256 or 512 consumer threads + 1 producer warp
 #define FS_MAX_CONSUMERS 512
 #define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
-#define FS_MAXDEG 8
+#define FS_MAXDEG 10                     // 1200x600, the gpu_fixed tree's default code (matrix/code.h:1), has rows of degree 9
 #define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
 #define FS_FWD 4                         // rows whose outputs stay in the forwarding ring
 #define FS_F_HAZARD 0x80000000u          // pos2 flags: not prefetched (written within the hazard window) ...
-#define FS_F_FWD    0x40000000u          // ... and the writer is at most FS_FWD rows back: bits 29..28 = rows back - 1, bits 27..25 = its edge slot
-#define FS_IDX_MASK 0x01FFFFFFu
+#define FS_F_FWD    0x40000000u          // ... and the writer is at most FS_FWD rows back: bits 29..28 = rows back - 1, bits 27..24 = its edge slot
+#define FS_IDX_MASK 0x00FFFFFFu
 
 struct FsArgs {
     uint32_t* V;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e
     for (int j = 0; j < D; j++) {
         if (p2[j] & FS_F_HAZARD) {
             if ((p2[j] & FS_F_FWD) && fwd_ok) {
-                const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 25) & 7u;
+                const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 24) & 15u;
                 wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * NC + tid) * 4u);
             } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
         } else wv[j] = lds_u32(stage_s + j * LINE + 4 * tid);
@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constan
     __syncthreads();
 
     if (warp == NC / 32) {
-        // ---------------- producer warp: lanes 0-7 fetch the posterior lines, lanes 8-15 the message lines of one row ----------
+        // ---------------- producer warp: lanes 0-15 fetch the posterior lines, lanes 16-31 the message lines of one row --------
         int stage = 0; uint32_t phase = 0;
-        const int j = lane & 7;
+        const int j = lane & 15;
         for (int it = 0; it < A.iters; it++) {
             size_t e = 0;
             for (int c = 0; c < A.nb_deg; c++) {
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constan
                 for (int r = 0; r < A.rows[c]; r++, e += D) {
                     if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
                     __syncwarp();
-                    const uint32_t p2 = (lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : 0x80000000u;
-                    const bool do_v = lane < 8 && j < D && !(p2 & FS_F_HAZARD);
-                    const bool do_m = lane >= 8 && lane < 16 && j < D && it > 0;
+                    const uint32_t p2 = (j < D) ? __ldg(A.pos2 + e + j) : 0x80000000u;
+                    const bool do_v = lane < 16 && j < D && !(p2 & FS_F_HAZARD);
+                    const bool do_m = lane >= 16 && j < D && it > 0;
                     const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, do_v || do_m));
                     const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
                     if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constan
         if (it == 0) { if (quirk) fs_row<SEM, ALGO, DD, true, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, true, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
         else         { if (quirk) fs_row<SEM, ALGO, DD, false, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, false, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
         break;
-                switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) }
+                switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
 #undef FS_CASE
                 prev_empty = bars + 8 * (Kst + stage); q++;
                 if (++stage == Kst) { stage = 0; phase ^= 1u; }

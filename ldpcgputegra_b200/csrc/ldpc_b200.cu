@@ -651,7 +651,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         bool ok = params->early_term == LDPC_ET_NONE && code->n_checks >= 8 * FS_HAZARD;
         int dmax = 0;
         for (int i = 0; i < code->nb_deg; i++) { ok = ok && code->deg[i] >= 3 && code->deg[i] <= FS_MAXDEG && code->n <= (int)FS_IDX_MASK; dmax = std::max(dmax, code->deg[i]); }
-        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs early_term off, row degrees 3..8 and >= 128 rows"); }
+        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs early_term off, row degrees 3..10 and >= 128 rows"); }
         if (ok && params->kernel != 1) {
             // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
             std::vector<uint32_t> pos2((size_t)code->m);
@@ -667,7 +667,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
                             if (lap == 1) {
                                 uint32_t w = v;
                                 if (back <= FS_HAZARD) w |= FS_F_HAZARD;
-                                if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << 25);
+                                if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << 24);
                                 pos2[e] = w;
                             }
                             last[v] = q; last_slot[v] = j;
