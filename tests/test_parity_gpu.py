@@ -323,3 +323,22 @@ def test_four_decoder_objects_on_four_host_threads(code576):
     assert not errors, errors
     for i in range(4):
         assert np.array_equal(results[i], expect[i]), f"thread {i} ({cfgs[i]})"
+
+
+@pytest.mark.parametrize("name", ["2304x1152", "1248x624", "1944x972"])
+def test_large_step_plans_with_early_termination_and_packing(built, name):
+    """The 64-128-row steps of the on-chip plan (one frame pair over 2-4 warps): early termination with iteration counts, packed
+    output, odd frame counts, and the 32-row-step plan of the same code as a cross-check."""
+    c = Code.load(name)
+    llr = np.concatenate([awgn_llr(c, 61, 2.5, 501), awgn_llr(c, 30, 1.0, 502), stress_llr(c, 12, 503)])
+    for kw in (dict(algo="OMS", semantics="ARM_SCALAR", early_term=1), dict(algo="OMS", semantics="X86_SSE", early_term=1), dict(algo="NMS", semantics="GPU_FIXED")):
+        g = gpu_decode(c, llr, 20, want_iters=True, **kw)
+        assert g["kernel"] == 2
+        o = oracle_decode(c, g["prm"], llr, 20)
+        assert_same(g, o, f"{name} {kw}")
+        assert np.array_equal(g["iters"], o["iters"])
+        g2 = gpu_decode(c, llr, 20, want_iters=True, small_steps=1, **kw)
+        assert_same(g2, o, f"{name} {kw} small steps")
+    dec = pkg.CGPUDecoder(c, nb_frames=128, out_format=1)
+    assert np.array_equal(dec.decode(llr, 6), oracle_pack(oracle_decode(c, dec.params, llr, 6)["hard"], c.n))
+    dec.close()
