@@ -25,7 +25,9 @@
 
 namespace ldpcb200 {
 
-#define FS_CONSUMERS 128                 // granularity of the state arrays' row pitch (words); a CTA has NC = 128, 256 or 512 consumer threads + 1 producer warp
+#define FS_CONSUMERS 128                 // granularity of the state arrays' row pitch (words); a CTA has NC = 128, 256 or 512 consumer threads + 2 producer warps
+#define FS_PRODUCER_THREADS 64           // one warp fetches the posterior lines, one the message lines: a bulk copy costs ~46 issue cycles, and
+                                         // the single producer of the first version (1340 cycles per row) bounded small batches
 #define FS_MAX_CONSUMERS 512
 #define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
 #define FS_MAXDEG 10                     // 1200x600, the gpu_fixed tree's default code (matrix/code.h:1), has rows of degree 9
@@ -101,7 +103,7 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e
 }
 
 template <int SEM, int ALGO, int NC>
-__global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constant__ FsArgs A)
+__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];
@@ -114,13 +116,15 @@ __global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * NC;
     if (threadIdx.x == 0) {
-        for (int k = 0; k < Kst; k++) { mbar_init(bars + 8 * k, 1); mbar_init(bars + 8 * (Kst + k), NC / 32); }
+        for (int k = 0; k < Kst; k++) { mbar_init(bars + 8 * k, 2); mbar_init(bars + 8 * (Kst + k), NC / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == NC / 32) {
-        // ---------------- producer warp: lanes 0-15 fetch the posterior lines, lanes 16-31 the message lines of one row --------
+    if (warp >= NC / 32) {
+        // ---------------- two producer warps: warp NC/32 fetches the posterior lines of every row, warp NC/32 + 1 its message lines.
+        // Both arrive on the stage's "full" barrier (count 2) with their own byte counts.
+        const bool msg_side = warp > NC / 32;
         int stage = 0; uint32_t phase = 0;
         const int j = lane & 15;
         for (int it = 0; it < A.iters; it++) {
@@ -128,17 +132,18 @@ __global__ void __launch_bounds__(NC + 32) fs_decode_kernel(const __grid_constan
             for (int c = 0; c < A.nb_deg; c++) {
                 const int D = A.deg[c];
                 for (int r = 0; r < A.rows[c]; r++, e += D) {
+                    const uint32_t p2 = (!msg_side && lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : FS_F_HAZARD;     // issued before the wait: the latencies overlap
                     if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
                     __syncwarp();
-                    const uint32_t p2 = (j < D) ? __ldg(A.pos2 + e + j) : 0x80000000u;
-                    const bool do_v = lane < 16 && j < D && !(p2 & FS_F_HAZARD);
-                    const bool do_m = lane >= 16 && j < D && it > 0;
-                    const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, do_v || do_m));
+                    const bool go = msg_side ? (lane < 16 && j < D && it > 0) : !(p2 & FS_F_HAZARD);
+                    const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
                     const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
                     if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
                     __syncwarp();
-                    if (do_v) bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
-                    if (do_m) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                    if (go) {
+                        if (msg_side) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                        else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
+                    }
                     if (++stage == Kst) { stage = 0; phase ^= 1u; }
                 }
             }

@@ -54,7 +54,7 @@ static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
 #define FS_LAUNCH(NCV)                                                                                                                  \
     { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
       if (e != cudaSuccess) return (int)e;                                                                                                 \
-      fs_decode_kernel<SEM, ALGO, NCV><<<blocks, NCV + 32, smem, st>>>(a); }
+      fs_decode_kernel<SEM, ALGO, NCV><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
     if (a.nc == 512) FS_LAUNCH(512) else if (a.nc == 256) FS_LAUNCH(256) else FS_LAUNCH(128)
 #undef FS_LAUNCH
     return (int)cudaGetLastError();
