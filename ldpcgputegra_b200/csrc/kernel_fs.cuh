@@ -79,14 +79,21 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e
     uint32_t p2[D], wv[D], wm[D], nv[D], nm[D];
 #pragma unroll
     for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
+    // The stage word is always loaded (a valid shared-memory address whatever the flags say); the row's hazards are patched in
+    // behind ONE warp-uniform test of the OR of the flags, so rows without hazards run branch-free (A/B: 4000x2000 -10 %).
+    uint32_t any = 0u;
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-        if (p2[j] & FS_F_HAZARD) {
-            if ((p2[j] & FS_F_FWD) && fwd_ok) {
-                const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 24) & 15u;
-                wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * NC + tid) * 4u);
-            } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
-        } else wv[j] = lds_u32(stage_s + j * LINE + 4 * tid);
+    for (int j = 0; j < D; j++) { wv[j] = lds_u32(stage_s + j * LINE + 4 * tid); any |= p2[j]; }
+    if (any & FS_F_HAZARD) {
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            if (p2[j] & FS_F_HAZARD) {
+                if ((p2[j] & FS_F_FWD) && fwd_ok) {
+                    const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 24) & 15u;
+                    wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * NC + tid) * 4u);
+                } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
+            }
+        }
     }
 #pragma unroll
     for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * LINE + 4 * tid);
