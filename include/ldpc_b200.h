@@ -112,7 +112,9 @@ typedef struct {
                              3 = generic engine (fp32 arithmetic: int16 / float / flooding, and int8 layered as a cross-check);
                              4 = frame-parallel with the state staged through shared memory by cp.async.bulk (long codes);
                              5 = generic engine with the state on chip (int16 / float / flooding on short codes) */
-    int32_t reserved[5];
+    int32_t reserved[5];  /* 0 for production use.  Experiment knobs of this implementation, used by tools/ and the A/B tests only:
+                             [0],[1] = (warps, pairs) of an on-chip group; [2] = kernel waves per pipeline chunk of decode();
+                             [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping; [4] = stage-ring depth */
 } ldpc_params_t;
 
 typedef struct ldpc_b200_handle_s* ldpc_handle;

@@ -209,9 +209,6 @@ def default_params(**kw) -> ParamsT:
         if k == "chunk_waves":    # waves per pipeline chunk of decode() (experiment knob)
             p.reserved[2] = v
             continue
-        if k == "fs_nc":          # consumer threads per CTA of the staged frame-parallel kernel: 128 / 256 / 512 (A/B experiments; shares reserved[3] with no_static)
-            p.reserved[3] = int(v)
-            continue
         if k == "fs_stages":      # ring depth of the staged frame-parallel kernel (A/B experiments)
             p.reserved[4] = int(v)
             continue

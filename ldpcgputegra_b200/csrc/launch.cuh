@@ -55,7 +55,7 @@ static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
     { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
       if (e != cudaSuccess) return (int)e;                                                                                                 \
       fs_decode_kernel<SEM, ALGO, NCV><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
-    if (a.nc == 512) FS_LAUNCH(512) else if (a.nc == 256) FS_LAUNCH(256) else FS_LAUNCH(128)
+    FS_LAUNCH(128)      // 256- and 512-consumer CTAs were measured not to matter and are no longer instantiated
 #undef FS_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -434,8 +434,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     }
     // frame-parallel: interleave -> decode -> de-interleave + hard decision
     const size_t t4 = (frames + 3) / 4;
-    const int knob = h->prm.reserved[3];
-    const int tq = h->kernel != 4 ? 32 : (knob == 128 || knob == 256 || knob == 512) ? knob : FS_CONSUMERS;
+    const int tq = h->kernel != 4 ? 32 : FS_CONSUMERS;
     const int T = (int)((t4 + tq - 1) / tq * tq);
     int rc;
     if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
@@ -462,7 +461,6 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         // test whether the copy engine's request rate bounds the kernel: it does not (DVB-S2, 256 Ki frames: 570 / 576 / 583 ms for
         // 128 / 256 / 512) — the consumers' issue slots do (profiles/r01_ncu_fs_v2.txt: 66 % issue-active, 636 warp instructions per row).
         int nc = 128;
-        if (h->prm.reserved[3] == 128 || h->prm.reserved[3] == 256 || h->prm.reserved[3] == 512) { if (T % h->prm.reserved[3] == 0) nc = h->prm.reserved[3]; }   // experiment knob
         f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
         const int ctas = T / nc, per_sm = std::min(4, (ctas + h->sms - 1) / h->sms);
@@ -683,7 +681,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     // pipeline granularity of decode(): a quarter of the declared capacity, at least one full wave of the chosen kernel
     // pipeline granularity of decode(): whole waves of the chosen kernel.  H2D, kernel and D2H take about the same time per
     // frame for 576x288 over PCIe Gen5, so the fill/drain of the 3-stage pipeline costs 2 chunks: many small chunks win
-    // (measured: 5 chunks 1.17 ms, 10 chunks of one wave each — see profiles/r01_e2e_chunks.txt).  reserved[2] overrides (waves per chunk).
+    // (measured with tools/e2e_sweep.py: 5 chunks 1.17 ms, 10 chunks of one wave each 1.11 ms).  reserved[2] overrides (waves per chunk).
     const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : h->kernel == 5 ? (size_t)h->sms * h->oc_F : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
     size_t k = h->kernel == 2 ? 1 : h->kernel == 5 ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
