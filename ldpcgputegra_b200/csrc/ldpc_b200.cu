@@ -736,6 +736,7 @@ int ldpc_b200_device_free(ldpc_handle h, void* p)
 int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters_done, void* cuda_stream)
 {
     if (!h || !d_llr || !d_hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode_device: bad argument");
+    if (d_iters_done && iters > 255) return fail(h, LDPC_ERR_INVALID, "iteration counts are returned as bytes: iters <= 255 when iters_done is requested");
     if (frames == 0) return LDPC_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
@@ -747,6 +748,7 @@ int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, s
 int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* hard, size_t frames, int iters, uint8_t* iters_done)
 {
     if (!h || slot < 0 || slot >= kSlots || !llr || !hard || iters < 0) return fail(h, LDPC_ERR_INVALID, "decode_async: bad argument");
+    if (iters_done && iters > 255) return fail(h, LDPC_ERR_INVALID, "iteration counts are returned as bytes: iters <= 255 when iters_done is requested");
     if (frames == 0) return LDPC_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     Slot& s = h->slot[slot];

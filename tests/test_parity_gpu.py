@@ -294,6 +294,20 @@ def test_dvbs2_full_batch_properties(built):
     dec.close()
 
 
+def test_argument_errors_return_codes_not_exits(code576):
+    """The reference exit(0)s on bad input (custom_cuda.cu:5-17); the library returns a status and keeps the handle usable."""
+    dec = pkg.CGPUDecoder(code576, nb_frames=64, device=0, early_term=1)
+    llr = awgn_llr(code576, 8, 2.0, 1)
+    with pytest.raises(pkg.LdpcError) as e:
+        dec.decode(llr, 300, want_iters=True)
+    assert e.value.status == pkg.ERR_INVALID and "255" in str(e.value)
+    with pytest.raises(pkg.LdpcError):
+        dec.decode(llr, -1)
+    hard, it = dec.decode(llr, 255, want_iters=True)              # still alive, and 255 iterations with early stop is fine
+    assert hard.shape == (8, 576) and it.max() <= 255
+    dec.close()
+
+
 def test_four_decoder_objects_on_four_host_threads(code576):
     """The reference harness runs 4 decoder objects in 4 OpenMP sections against one GPU (code/gpu_fixed/test.cpp:241-281,347-393):
     one handle per host thread, no shared mutable state.  Four threads decode different batches at once, several times over, with
