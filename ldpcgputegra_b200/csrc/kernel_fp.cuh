@@ -27,6 +27,7 @@ struct FpArgs {
     int deg[LDPC_MAX_DEG_CLASSES];
     int rows[LDPC_MAX_DEG_CLASSES];
     int iters;
+    uint32_t exp_word;       // 0x64646464 (rowops.cuh: bytes01_to_w)
     ldpc_params_t prm;
 };
 
@@ -46,9 +47,9 @@ __device__ __forceinline__ void fp_row_math(const uint32_t (&wv)[D], const uint3
         uint32_t f[D];
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            h2 wU = g ? bytes23_to_w(wv[j]) : bytes01_to_w(wv[j]);
+            h2 wU = g ? bytes23_to_w(wv[j], K.c64) : bytes01_to_w(wv[j], K.c64);
             h2 nM = m4;                                                        // -(0) - 4
-            if (!FIRST) { h2 wM = g ? bytes23_to_w(wm[j]) : bytes01_to_w(wm[j]); nM = __hfma2(wM, __hneg2(inv256), half); }
+            if (!FIRST) { h2 wM = g ? bytes23_to_w(wm[j], K.c64) : bytes01_to_w(wm[j], K.c64); nM = __hfma2(wM, __hneg2(inv256), half); }
             xu[j] = __hmin2(__hfma2_sat(wU, inv256, nM), K.top);               // clamp(v - m) in the biased domain
         }
         RowState s;
@@ -80,17 +81,20 @@ template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
 __device__ __forceinline__ void fp_row(const FpArgs& A, int t, size_t e, const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi)
 {
     uint32_t idx[D], wv[D], wm[D], nv[D], nm[D];
+    const uint32_t T4 = 4u * (uint32_t)A.T;
+    uint32_t* const vt = A.V + t;
+    uint32_t* const mp = A.MSG + (e * (size_t)A.T + (size_t)t);
 #pragma unroll
     for (int j = 0; j < D; j++) idx[j] = __ldg(A.pos + e + j);
 #pragma unroll
-    for (int j = 0; j < D; j++) wv[j] = A.V[(size_t)idx[j] * A.T + t];
+    for (int j = 0; j < D; j++) wv[j] = *word_at(vt, idx[j], T4);
 #pragma unroll
-    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : A.MSG[(e + j) * A.T + t];
+    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : *word_at(mp, (uint32_t)j, T4);
     fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        A.V[(size_t)idx[j] * A.T + t] = nv[j];
-        A.MSG[(e + j) * A.T + t] = nm[j];
+        *word_at(vt, idx[j], T4) = nv[j];
+        *word_at(mp, (uint32_t)j, T4) = nm[j];
     }
 }
 
@@ -105,8 +109,8 @@ __device__ __noinline__ void fp_row_generic(const FpArgs& A, int t, size_t e, in
         const uint32_t wm = FIRST ? 0x80808080u : A.MSG[(e + j) * A.T + t];
 #pragma unroll
         for (int g = 0; g < 2; g++) {
-            h2 wU = g ? bytes23_to_w(wv) : bytes01_to_w(wv);
-            h2 wM = g ? bytes23_to_w(wm) : bytes01_to_w(wm);
+            h2 wU = g ? bytes23_to_w(wv, K.c64) : bytes01_to_w(wv, K.c64);
+            h2 wM = g ? bytes23_to_w(wm, K.c64) : bytes01_to_w(wm, K.c64);
             h2 xu = __hmin2(__hfma2_sat(wU, inv256, __hfma2(wM, __hneg2(inv256), half)), K.top);
             pass1_edge<SEM, ALGO, Q>(s[g], xu, K);
         }
@@ -119,8 +123,8 @@ __device__ __noinline__ void fp_row_generic(const FpArgs& A, int t, size_t e, in
         uint32_t ov[2], om[2];
 #pragma unroll
         for (int g = 0; g < 2; g++) {
-            h2 wU = g ? bytes23_to_w(wv) : bytes01_to_w(wv);
-            h2 wM = g ? bytes23_to_w(wm) : bytes01_to_w(wm);
+            h2 wU = g ? bytes23_to_w(wv, K.c64) : bytes01_to_w(wv, K.c64);
+            h2 wM = g ? bytes23_to_w(wm, K.c64) : bytes01_to_w(wm, K.c64);
             h2 xu = __hmin2(__hfma2_sat(wU, inv256, __hfma2(wM, __hneg2(inv256), half)), K.top);
             h2 a = magnitude<SEM, ALGO, Q>(signed_contrib(xu, K), K);
             h2 msg, unew;
@@ -181,8 +185,8 @@ __device__ __forceinline__ void fp_syndrome(const FpArgs& A, int t, const RowCon
             for (int j = 0; j < D; j++, e++) {
                 const uint32_t wv = A.V[(size_t)__ldg(A.pos + e) * A.T + t];
                 const uint32_t wm = A.MSG[e * A.T + t];
-                h2 x0 = __hmin2(__hfma2_sat(bytes01_to_w(wv), inv256, __hfma2(bytes01_to_w(wm), __hneg2(inv256), half)), K.top);
-                h2 x1 = __hmin2(__hfma2_sat(bytes23_to_w(wv), inv256, __hfma2(bytes23_to_w(wm), __hneg2(inv256), half)), K.top);
+                h2 x0 = __hmin2(__hfma2_sat(bytes01_to_w(wv, K.c64), inv256, __hfma2(bytes01_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
+                h2 x1 = __hmin2(__hfma2_sat(bytes23_to_w(wv, K.c64), inv256, __hfma2(bytes23_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
                 p0 ^= h2_bits(__hadd2(x0, lo_np));
                 p1 ^= h2_bits(__hadd2(x1, lo_np));
             }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_decode_kernel(const __grid_consta
 {
     const int t = blockIdx.x * FP_BLOCK + threadIdx.x;
     if (t >= A.T) return;
-    RowConsts K; make_consts<SEM>(K, A.prm);
+    RowConsts K; make_consts<SEM>(K, A.prm); K.c64 = A.exp_word;
     const int lo = (SEM == LDPC_SEM_GPU_FIXED) ? -128 : -A.prm.sat_var;
     uint32_t keep_lo = 0u, keep_hi = 0u;           // 0xFFFF per half = frame frozen (early-terminated)
     uint32_t done[4] = { 0u, 0u, 0u, 0u };

@@ -35,7 +35,12 @@ namespace ldpcb200 {
 #define FS_FWD 4                         // rows whose outputs stay in the forwarding ring
 #define FS_F_HAZARD 0x80000000u          // pos2 flags: not prefetched (written within the hazard window) ...
 #define FS_F_FWD    0x40000000u          // ... and the writer is at most FS_FWD rows back: bits 29..28 = rows back - 1, bits 27..24 = its edge slot
-#define FS_IDX_MASK 0x00FFFFFFu
+#define FS_IDX_MASK 0x000FFFFFu
+// Row summary in bits 23..20 of the row's first three words (every row has >= 3 edges): word 0 = slot of the row's ONLY hazard edge
+// when that edge can be forwarded (14 = some other hazard pattern, 15 = no hazard), word 1 = the writer's slot, word 2 = rows back - 1.
+#define FS_ROW_SHIFT 20
+#define FS_ROW_NONE 15u
+#define FS_ROW_GENERIC 14u
 
 struct FsArgs {
     uint32_t* V;
@@ -45,6 +50,7 @@ struct FsArgs {
     int deg[LDPC_MAX_DEG_CLASSES];
     int rows[LDPC_MAX_DEG_CLASSES];
     int iters, stages, max_deg;
+    uint32_t exp_word;       // 0x64646464 (rowops.cuh: bytes01_to_w)
     int nc;                  // consumer threads per CTA (128 | 256 | 512): a staged line is nc * 4 bytes.  The bulk-copy engine serves a
                              // request in ~70 cycles whatever its size, so 512-byte lines cap the SM at ~7 B/clk (measured); wider CTAs lift that
     ldpc_params_t prm;
@@ -72,26 +78,35 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // The stage of the PREVIOUS row is handed back here, between this row's arithmetic and its stores: the fence then only has
 // to cover stores that were issued a whole row ago, so it never waits on fresh ones.
 template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC>
-__device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e, uint32_t stage_s, const RowConsts& K, uint32_t prev_empty, int lane,
-                                       uint32_t fwd_s, uint32_t q, bool fwd_ok)
+__device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, const uint32_t (&p2)[D], uint32_t stage_s, const RowConsts& K,
+                                       uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool fwd_ok)
 {
     constexpr uint32_t LINE = NC * 4u;
-    uint32_t p2[D], wv[D], wm[D], nv[D], nm[D];
+    uint32_t wv[D], wm[D], nv[D], nm[D];
+    // Hazards (edges the producer did not prefetch because one of the last FS_HAZARD rows wrote the variable).  The common pattern —
+    // exactly one such edge per row, its writer at most FS_FWD rows back: the staircase of DVB-S2 and of every IRA code — is
+    // served by copying the writer's word from the forwarding ring INTO the stage slot (shared memory takes a run-time slot
+    // number, a register array does not), after which the row loads all its words from the stage like a row without hazards.
+    // The per-edge flag tests of the first version cost ~40 issued instructions per row for one flagged edge; this costs ~12.
+    const uint32_t hs = (p2[0] >> FS_ROW_SHIFT) & 15u;
+    bool generic = false;
+    if (hs != FS_ROW_NONE) {
+        if (hs < FS_ROW_GENERIC && fwd_ok) {
+            const uint32_t ws = (p2[1] >> FS_ROW_SHIFT) & 15u, back = ((p2[2] >> FS_ROW_SHIFT) & 3u) + 1u;
+            const uint32_t v = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * (uint32_t)A.max_deg + ws) * NC + tid) * 4u);
+            sts_u32(stage_s + hs * LINE + 4 * tid, v);        // read back below by this same thread: program order
+        } else generic = true;
+    }
 #pragma unroll
-    for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
-    // The stage word is always loaded (a valid shared-memory address whatever the flags say); the row's hazards are patched in
-    // behind ONE warp-uniform test of the OR of the flags, so rows without hazards run branch-free (A/B: 4000x2000 -10 %).
-    uint32_t any = 0u;
-#pragma unroll
-    for (int j = 0; j < D; j++) { wv[j] = lds_u32(stage_s + j * LINE + 4 * tid); any |= p2[j]; }
-    if (any & FS_F_HAZARD) {
+    for (int j = 0; j < D; j++) wv[j] = lds_u32(stage_s + j * LINE + 4 * tid);
+    if (generic) {
 #pragma unroll
         for (int j = 0; j < D; j++) {
             if (p2[j] & FS_F_HAZARD) {
                 if ((p2[j] & FS_F_FWD) && fwd_ok) {
                     const uint32_t back = ((p2[j] >> 28) & 3u) + 1u, slot = (p2[j] >> 24) & 15u;
-                    wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * FS_MAXDEG + slot) * NC + tid) * 4u);
-                } else wv[j] = A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t];
+                    wv[j] = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * (uint32_t)A.max_deg + slot) * NC + tid) * 4u);
+                } else wv[j] = *word_at(vt, p2[j] & FS_IDX_MASK, T4);
             }
         }
     }
@@ -103,14 +118,46 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, int t, size_t e
     if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        A.V[(size_t)(p2[j] & FS_IDX_MASK) * A.T + t] = nv[j];
-        A.MSG[(e + j) * A.T + t] = nm[j];
-        sts_u32(fwd_s + (((q & (FS_FWD - 1)) * FS_MAXDEG + j) * NC + tid) * 4u, nv[j]);
+        *word_at(vt, p2[j] & FS_IDX_MASK, T4) = nv[j];          // vt = V + t, mp = MSG + e * T + t, T4 = 4 * T
+        *word_at(mp, (uint32_t)j, T4) = nm[j];
+        sts_u32(fwd_s + (((q & (FS_FWD - 1)) * (uint32_t)A.max_deg + j) * NC + tid) * 4u, nv[j]);
     }
 }
 
-template <int SEM, int ALGO, int NC>
-__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS) fs_decode_kernel(const __grid_constant__ FsArgs A)
+// consumer-side ring cursor
+struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
+
+// all rows of one degree class.  The row's edge words (variable index + hazard flags) are fetched ONE ROW AHEAD: they come from
+// global memory (L1 hit for 3 rows out of 4, L2 otherwise) and used to sit at the head of every row's dependency chain
+// (profiles/r01_ncu_fs_v2.txt: 15 % of the stall samples on the long scoreboard).  pos2 is padded by FS_MAXDEG words so that the
+// read past the last row is harmless; the words fetched across a class boundary are simply dropped.
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC>
+__device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
+                                         uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c)
+{
+    const uint32_t T4 = 4u * (uint32_t)A.T;
+    uint32_t* const vt = A.V + t;
+    uint32_t* mp = A.MSG + (e * (size_t)A.T + (size_t)t);
+    uint32_t p2[D], p2n[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
+    for (int r = 0; r < R; r++, e += D) {
+#pragma unroll
+        for (int j = 0; j < D; j++) p2n[j] = __ldg(A.pos2 + e + D + j);
+        mbar_wait(bars + 8 * c.stage, c.phase);
+        fs_row<SEM, ALGO, D, FIRST, Q, NC>(A, tid, vt, mp, T4, p2, ring + (uint32_t)c.stage * stage_bytes, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD);
+        mp = word_at(mp, (uint32_t)D, T4);
+        c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
+        if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
+#pragma unroll
+        for (int j = 0; j < D; j++) p2[j] = p2n[j];
+    }
+}
+
+// MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
+// body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
+template <int SEM, int ALGO, int NC, int MAXD>
+__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];
@@ -118,7 +165,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS) fs_decode_kernel(con
     const int Kst = A.stages;
     const uint32_t bars = smem_u32(fs_smem);
     const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
-    const uint32_t ring = fwd_s + FS_FWD * FS_MAXDEG * LINE;
+    const uint32_t ring = fwd_s + FS_FWD * (uint32_t)A.max_deg * LINE;
     const uint32_t stage_bytes = (uint32_t)(2 * A.max_deg) * LINE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * NC;
@@ -160,29 +207,26 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS) fs_decode_kernel(con
 
     // ---------------- consumers ---------------------------------------------------------------------------------------------
     const int tid = threadIdx.x, t = t0 + tid;
-    RowConsts K; make_consts<SEM>(K, A.prm);
-    int stage = 0; uint32_t phase = 0, prev_empty = 0u, q = 0u;
+    RowConsts K; make_consts<SEM>(K, A.prm); K.c64 = A.exp_word;
+    FsCursor cur{0, 0u, 0u, 0u};
     for (int it = 0; it < A.iters; it++) {
         size_t e = 0;
         for (int c = 0; c < A.nb_deg; c++) {
-            const int D = A.deg[c];
+            const int D = A.deg[c], R = A.rows[c];
             const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
             // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
             K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
-            for (int r = 0; r < A.rows[c]; r++, e += D) {
-                mbar_wait(bars + 8 * stage, phase);
-                const bool fwd_ok = q >= FS_FWD;            // the first rows of the first iteration have no predecessors in the ring
-                const uint32_t st_s = ring + (uint32_t)stage * stage_bytes;
-#define FS_CASE(DD)                                                                                                   \
-    case DD:                                                                                                          \
-        if (it == 0) { if (quirk) fs_row<SEM, ALGO, DD, true, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, true, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
-        else         { if (quirk) fs_row<SEM, ALGO, DD, false, true, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); else fs_row<SEM, ALGO, DD, false, false, NC>(A, tid, t, e, st_s, K, prev_empty, lane, fwd_s, q, fwd_ok); } \
+#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC>(A, tid, t, e, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur)
+#define FS_CASE(DD)                                                                          \
+    case DD:                                                                                 \
+        if constexpr (DD <= MAXD) {                                                          \
+        if (it == 0) { if (quirk) FS_GO(DD, true, true); else FS_GO(DD, true, false); }      \
+        else         { if (quirk) FS_GO(DD, false, true); else FS_GO(DD, false, false); }    \
+        }                                                                                    \
         break;
-                switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
+            switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
 #undef FS_CASE
-                prev_empty = bars + 8 * (Kst + stage); q++;
-                if (++stage == Kst) { stage = 0; phase ^= 1u; }
-            }
+#undef FS_GO
         }
     }
 }

@@ -51,11 +51,14 @@ static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStre
 template <int SEM, int ALGO>
 static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
 {
-#define FS_LAUNCH(NCV)                                                                                                                  \
-    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+#define FS_LAUNCH(NCV, MD)                                                                                                              \
+    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return (int)e;                                                                                                 \
-      fs_decode_kernel<SEM, ALGO, NCV><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
-    FS_LAUNCH(128)      // 256- and 512-consumer CTAs were measured not to matter and are no longer instantiated
+      fs_decode_kernel<SEM, ALGO, NCV, MD><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
+    // CTA width x widest row body.  The kernel's registers are those of its widest body, and the two producer warps get the same
+    // allocation as the consumers: 256 consumers per CTA keep 16 consumer warps on an SM where 128 keep 12
+    if (a.nc == 256) { if (a.max_deg <= 8) FS_LAUNCH(256, 8) else FS_LAUNCH(256, FS_MAXDEG) }
+    else             { if (a.max_deg <= 8) FS_LAUNCH(128, 8) else FS_LAUNCH(128, FS_MAXDEG) }
 #undef FS_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -434,7 +434,14 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     }
     // frame-parallel: interleave -> decode -> de-interleave + hard decision
     const size_t t4 = (frames + 3) / 4;
-    const int tq = h->kernel != 4 ? 32 : FS_CONSUMERS;
+    // consumer threads per CTA of the staged kernel.  The kernel's registers (96 for rows up to degree 8) keep 2 CTAs of 256 + 64
+    // threads on an SM (16 consumer warps) or, capped at 80 registers with a few spills, 4 CTAs of 128 + 64 (16 consumer warps, twice
+    // the producers).  A/B on one box, DVB-S2: 256 Ki frames 464 vs 493 ms, 128 Ki 276 vs 260 ms, 64 Ki 274 vs 209 ms — the wide
+    // CTA wins once there are two of them for every SM.  reserved[4] bits 8.. force 128 (1) or 256 (2).
+    const size_t fs_words = (t4 + 255) / 256 * 256;
+    const int fs_nc = (h->prm.reserved[4] >> 8) == 2 ? 256 : (h->prm.reserved[4] >> 8) == 1 ? FS_CONSUMERS
+                    : (fs_words / 256 >= (size_t)(2 * h->sms * 17 / 20) ? 256 : FS_CONSUMERS);
+    const int tq = h->kernel != 4 ? 32 : fs_nc;
     const int T = (int)((t4 + tq - 1) / tq * tq);
     int rc;
     if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
@@ -446,7 +453,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     FpArgs a{};
     a.V = s.d_V; a.MSG = s.d_MSG; a.pos = h->d_pos; a.iters_done = nullptr; a.T = T; a.n = c.n; a.m = c.m; a.nb_deg = c.nb_deg;
     for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { a.deg[i] = c.deg[i]; a.rows[i] = c.rows[i]; }
-    a.iters = iters; a.prm = h->prm;
+    a.iters = iters; a.exp_word = 0x64646464u; a.prm = h->prm;
     uint8_t* d_it4 = nullptr;
     if (d_iters) {   // kernel writes 4*T entries (padding frames included) into the slot's scratch, then the valid part is copied
         if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (size_t)4 * T))) return rc;
@@ -456,18 +463,18 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         FsArgs f{};
         f.V = s.d_V; f.MSG = s.d_MSG; f.pos2 = h->d_pos2; f.T = T; f.n = c.n; f.m = c.m; f.nb_deg = c.nb_deg;
         for (int i = 0; i < LDPC_MAX_DEG_CLASSES; i++) { f.deg[i] = c.deg[i]; f.rows[i] = c.rows[i]; }
-        f.iters = iters; f.max_deg = h->fs_max_deg; f.prm = h->prm;
+        f.iters = iters; f.max_deg = h->fs_max_deg; f.exp_word = 0x64646464u; f.prm = h->prm;
         // consumers per CTA: 128.  Wider CTAs (256 / 512 consumers = 1 KB / 2 KB lines, a quarter of the bulk-copy requests) were built to
         // test whether the copy engine's request rate bounds the kernel: it does not (DVB-S2, 256 Ki frames: 570 / 576 / 583 ms for
         // 128 / 256 / 512) — the consumers' issue slots do (profiles/r01_ncu_fs_v2.txt: 66 % issue-active, 636 warp instructions per row).
-        int nc = 128;
+        const int nc = fs_nc;
         f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
-        const int ctas = T / nc, per_sm = std::min(4, (ctas + h->sms - 1) / h->sms);
-        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)2 * f.max_deg * line, fwd_bytes = (size_t)FS_FWD * FS_MAXDEG * line;
+        const int ctas = T / nc, per_sm = std::min(nc == 128 ? 4 : 2, (ctas + h->sms - 1) / h->sms);
+        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)2 * f.max_deg * line, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
-        if (h->prm.reserved[4] >= 2 && h->prm.reserved[4] < FS_HAZARD) stages = h->prm.reserved[4];     // experiment knob
+        if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob
         f.stages = stages;
         const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + fwd_bytes + stages * stage_bytes;
         fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fs_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fs_uniform
@@ -652,24 +659,33 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs early_term off, row degrees 3..10 and >= 128 rows"); }
         if (ok && params->kernel != 1) {
             // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
-            std::vector<uint32_t> pos2((size_t)code->m);
+            std::vector<uint32_t> pos2((size_t)code->m + FS_MAXDEG, 0u);      // padded: the consumers fetch one row ahead
             std::vector<long> last((size_t)code->n, -(long)(1 << 30));
             std::vector<int> last_slot((size_t)code->n, 0);
             for (int lap = 0; lap < 2; lap++) {
                 long q = (long)lap * code->n_checks; size_t e = 0;
                 for (int k = 0; k < code->nb_deg; k++)
-                    for (int r = 0; r < code->rows[k]; r++, q++)
+                    for (int r = 0; r < code->rows[k]; r++, q++) {
+                        const size_t e0 = e;
+                        int nhaz = 0, hslot = 0, wslot = 0; long hback = 0; bool fwd = false;
                         for (int j = 0; j < code->deg[k]; j++, e++) {
                             const uint32_t v = code->pos[e];
                             const long back = q - last[v];
                             if (lap == 1) {
                                 uint32_t w = v;
-                                if (back <= FS_HAZARD) w |= FS_F_HAZARD;
+                                if (back <= FS_HAZARD) { w |= FS_F_HAZARD; nhaz++; hslot = j; wslot = last_slot[v]; hback = back; fwd = back <= FS_FWD; }
                                 if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << 24);
                                 pos2[e] = w;
                             }
                             last[v] = q; last_slot[v] = j;
                         }
+                        if (lap == 1) {     // row summary (kernel_fs.cuh: FS_ROW_SHIFT)
+                            const uint32_t hs = nhaz == 0 ? FS_ROW_NONE : (nhaz == 1 && fwd) ? (uint32_t)hslot : FS_ROW_GENERIC;
+                            pos2[e0] |= hs << FS_ROW_SHIFT;
+                            pos2[e0 + 1] |= (uint32_t)wslot << FS_ROW_SHIFT;
+                            pos2[e0 + 2] |= (uint32_t)(hback > 0 ? (hback - 1) & 3 : 0) << FS_ROW_SHIFT;
+                        }
+                    }
             }
             CREATE_TRY(cudaMalloc((void**)&h->d_pos2, pos2.size() * sizeof(uint32_t)));
             CREATE_TRY(cudaMemcpy(h->d_pos2, pos2.data(), pos2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -37,6 +37,7 @@ struct RowConsts {
     h2 k256;       // 256.0
     h2 one;        // 1.0
     uint32_t num1, sh1, num2, sh2;   // NMS rescale of min2 (-> c1) and min1 (-> c2): (k*num)>>sh
+    uint32_t c64;  // 0x64646464, from a kernel argument (see bytes01_to_w)
 };
 
 template <int SEM>
@@ -54,6 +55,7 @@ __device__ __forceinline__ void make_consts(RowConsts& K, const ldpc_params_t& p
     const int mi = (SEM == LDPC_SEM_ARM_SCALAR) ? p.sat_var + 1 : ((SEM == LDPC_SEM_GPU_FIXED) ? 127 : p.sat_var);
     K.min_init = h2_const((float)mi / 256.0f);
     K.k256 = h2_const(256.0f);
+    K.c64 = 0x64646464u;       // the frame-parallel kernels overwrite this with their exp_word argument
     K.one = h2_const(1.0f);
     if (SEM == LDPC_SEM_GPU_FIXED) {
         // trunc(min*0.75f) = (3*min)>>2 ; trunc(min*0.875f) = (7*min)>>3  (ref: CUDA_NMS_SIMD.cu:76-83, CUDA_2NMS_SIMD.cu:76-83)
@@ -223,8 +225,12 @@ __device__ __forceinline__ void pass2_edge(h2 xu, h2 a, const RowOut& o, const R
 
 // ---- storage conversions -------------------------------------------------------------------------------------------
 // A byte b in [0,255] becomes the binary16 number 1024+b by byte-permuting it under the exponent byte 0x64.
-__device__ __forceinline__ h2 bytes01_to_w(uint32_t word) { return bits_h2(__byte_perm(word, 0x64646464u, 0x4140)); }
-__device__ __forceinline__ h2 bytes23_to_w(uint32_t word) { return bits_h2(__byte_perm(word, 0x64646464u, 0x4342)); }
+// PRMT encodes ONE immediate: with the literal 0x64646464 as the second source ptxas keeps the SELECTOR in a register and
+// re-materialises it before every use (first SASS of kernel_fs: 25 extra moves per degree-7 row; an asm "mov" is folded just the
+// same).  The exponent word therefore arrives as a kernel argument (RowConsts::c64, host-set to 0x64646464), which ptxas cannot
+// fold, and the selector becomes the immediate.
+__device__ __forceinline__ h2 bytes01_to_w(uint32_t word, uint32_t c64) { return bits_h2(__byte_perm(word, c64, 0x4140)); }
+__device__ __forceinline__ h2 bytes23_to_w(uint32_t word, uint32_t c64) { return bits_h2(__byte_perm(word, c64, 0x4342)); }
 // w = 1024 + b  ->  b/256
 __device__ __forceinline__ h2 w_to_q(h2 w) { return __hfma2(w, h2_const(1.0f / 256.0f), h2_const(-4.0f)); }
 // q (multiple of 1/256, integer part q*256 + bias in [0,255]) -> binary16 bits 0x6400|byte
@@ -238,6 +244,13 @@ __device__ __forceinline__ uint32_t bias_bytes(uint32_t w, int lo, int hi)
     const uint32_t L = (uint32_t)(lo & 0xFF) * 0x01010101u, H = (uint32_t)(hi & 0xFF) * 0x01010101u;
     w = __vmaxs4(__vmins4(w, H), L);
     return __vsub4(w, L);
+}
+
+// base + idx * pitch_bytes, written so that it compiles to ONE instruction (IMAD.WIDE.U32 with the 64-bit base as addend).
+// V[(size_t)idx * T + t] with an int T costs five (wide multiply, high-part multiply for the sign extension, shift pair, add pair).
+__device__ __forceinline__ uint32_t* word_at(uint32_t* base, uint32_t idx, uint32_t pitch_bytes)
+{
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + (uint64_t)idx * (uint64_t)pitch_bytes);
 }
 
 // Shared memory is addressed through 32-bit shared-window offsets and explicit ld/st.shared in the hot loop: generic 64-bit

@@ -100,9 +100,10 @@ def test_other_codes(built, name):
         g1 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=1)
         assert_same(g1, o, f"{name} {sem}/{algo} kernel 1")
         if c.n_checks >= 128 and max(c.deg) <= 10 and min(c.deg) >= 3:     # the bulk-copy-staged frame-parallel kernel
-            g4 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=4)
-            assert g4["kernel"] == 4
-            assert_same(g4, o, f"{name} {sem}/{algo} kernel 4")
+            for nc in (128, 256):
+                g4 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=4, fs_nc=nc)
+                assert g4["kernel"] == 4
+                assert_same(g4, o, f"{name} {sem}/{algo} kernel 4 NC{nc}")
     gold = GOLD / f"k4_{name}_x86sse.npz"
     if gold.exists():
         gg = np.load(gold)
@@ -110,14 +111,15 @@ def test_other_codes(built, name):
         assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 4])
+@pytest.mark.parametrize("kernel", [0, 1, 4, 4256])
 def test_dvbs2_long_code_frame_parallel(built, kernel):
     """DVB-S2 64800x32400 (a 32 399-deep chain in reference order) against the reference's own x86 decoder (golden fixture):
     plain frame-parallel kernel (1), bulk-copy-staged kernel (4), and whatever the library picks (0 -> 4)."""
     c = Code.load("64800x32400")
     gg = np.load(GOLD / "k4_64800x32400_x86sse.npz")
-    r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", kernel=kernel)
-    assert r["kernel"] == (kernel or 4)
+    kw = dict(kernel=4, fs_nc=256) if kernel == 4256 else dict(kernel=kernel)      # 4256: kernel 4 with 256-consumer CTAs
+    r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", **kw)
+    assert r["kernel"] == (kw["kernel"] or 4)
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
     import hashlib
     assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg["OMS_1_10_sha"])
@@ -127,14 +129,15 @@ def test_dvbs2_long_code_frame_parallel(built, kernel):
 def test_staged_kernel_all_semantics(code576, sem, algo):
     """kernel 4 on a batch that spans several CTAs and a ragged tail, every (semantics, algorithm) pair, stage ring depths 2..15"""
     llr = np.concatenate([awgn_llr(code576, 700, 2.0, 241), stress_llr(code576, 333, 243, full_range=(sem == "GPU_FIXED"))])
-    for iters, stages in ((1, 0), (10, 0), (3, 2), (3, 15)):
-        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, want_iters=True)
+    for iters, stages, nc in ((1, 0, 128), (10, 0, 128), (3, 2, 128), (3, 15, 128), (10, 0, 256), (3, 2, 256), (2, 9, 256)):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, want_iters=True)
         assert g["kernel"] == 4 and (g["iters"] == iters).all()
-        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"staged {sem}/{algo} I{iters} K{stages}")
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"staged {sem}/{algo} I{iters} K{stages} NC{nc}")
     if (sem, algo) in (("X86_SSE", "OMS"), ("GPU_FIXED", "2NMS")):        # several CTAs + a ragged tail
         big = np.concatenate([llr, llr[::-1], llr[:700]])                  # 2766 frames -> 692 words per row -> 6 CTAs of 128 consumers
-        g = gpu_decode(code576, big, 4, algo=algo, semantics=sem, kernel=4)
-        assert_same(g, oracle_decode(code576, default_params(algo=algo, semantics=sem), big, 4), f"staged {sem}/{algo} 6 CTAs")
+        for nc in (128, 256):
+            g = gpu_decode(code576, big, 4, algo=algo, semantics=sem, kernel=4, fs_nc=nc)
+            assert_same(g, oracle_decode(code576, default_params(algo=algo, semantics=sem), big, 4), f"staged {sem}/{algo} 6 CTAs NC{nc}")
     with pytest.raises(pkg.LdpcError):
         pkg.CGPUDecoder(code576, nb_frames=64, device=0, kernel=4, early_term=1)
 

@@ -3,7 +3,7 @@
 engine — one JSON line in bench.py's contract (value / roofline / e2e / cpu_baseline), separate from bench.py so that the
 driver's flagship line stays untouched.
 
-  python tools/bench_dvbs2.py [--frames 262144] [--steps 3] [--warmup 3]            (torchrun for N > 1: frames are per GPU)
+  python tools/bench_dvbs2.py [--frames 303104] [--steps 3] [--warmup 3]            (torchrun for N > 1: frames are per GPU)
 
 A step = one decode of `frames` AWGN frames per GPU, 10 iterations, int8 layered OMS, x86-SSE semantics.  Algorithmic HBM bytes
 per frame: N in + N out + I * 4 * M (posterior r/w + message r/w per edge) = 9.20 MB; roofline = that / time against
@@ -20,7 +20,7 @@ CODE, ITERS, EBN0 = "64800x32400", 10, 2.0
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=262144)
+    ap.add_argument("--frames", type=int, default=303104)    # 148 SMs x 2 CTAs x 256 consumer threads x 4 frames: every SM carries the same load
     ap.add_argument("--e2e-frames", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)

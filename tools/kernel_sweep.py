@@ -28,7 +28,9 @@ def run(code_name, frames, iters, reps=12, rotate=6, **kw):
     fe = int(d_hard[:, :code.k_info].any(dim=1).sum())
     out = dict(code=code_name, frames=frames, iters=iters, ms=ms, mframes_s=frames / ms / 1e3, info_gbps=frames * code.k_info / ms / 1e6,
                kernel_used=dec.info(pkg.INFO_KERNEL), frames_per_cta=dec.info(pkg.INFO_FRAMES_PER_CTA), smem=dec.info(pkg.INFO_SMEM_BYTES), fer=fe / frames, rotate=rotate, **{k: str(v) for k, v in kw.items()})
-    print(json.dumps(out)); dec.close()
+    print(json.dumps(out), flush=True); dec.close()
+    del d_llrs, d_hard
+    torch.cuda.empty_cache()
 
 if __name__ == "__main__":
     import argparse
