@@ -439,7 +439,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     // the producers).  A/B on one box, DVB-S2: 256 Ki frames 464 vs 493 ms, 128 Ki 276 vs 260 ms, 64 Ki 274 vs 209 ms — the wide
     // CTA wins once there are two of them for every SM.  reserved[4] bits 8.. force 128 (1) or 256 (2).
     const size_t fs_words = (t4 + 255) / 256 * 256;
-    const int fs_nc = (h->prm.reserved[4] >> 8) == 2 ? 256 : (h->prm.reserved[4] >> 8) == 1 ? FS_CONSUMERS
+    const int fs_knob = h->prm.reserved[4] >> 8;
+    const int fs_nc = fs_knob == 3 && h->fs_max_deg <= 8 ? 320 : fs_knob == 2 ? 256 : fs_knob == 1 ? FS_CONSUMERS
                     : (fs_words / 256 >= (size_t)(2 * h->sms * 17 / 20) ? 256 : FS_CONSUMERS);
     const int tq = h->kernel != 4 ? 32 : fs_nc;
     const int T = (int)((t4 + tq - 1) / tq * tq);
@@ -470,7 +471,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         const int nc = fs_nc;
         f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
-        const int ctas = T / nc, per_sm = std::min(nc == 128 ? 4 : 2, (ctas + h->sms - 1) / h->sms);
+        const int ctas = T / nc, per_sm = std::min(nc == 128 ? 4 : 2, std::max(1, (ctas + h->sms - 1) / h->sms));
         const size_t line = (size_t)nc * 4, stage_bytes = (size_t)2 * f.max_deg * line, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
