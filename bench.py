@@ -141,7 +141,17 @@ def cpu_reference_run(llr: np.ndarray, min_seconds: float, threads: int):
     return F * reps / max(spent, 1e-9), kind, f"{F} frames x {reps} passes ({spent:.1f} s wall on {threads} threads)", hard
 
 
+def claim_stdout():
+    """Rank 0 must print ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there
+    when the communicator is created), so fd 1 is pointed at stderr for the whole run and the line goes to a private duplicate."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -186,7 +196,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "Gb/s", "cores": threads, "kind": kind, "sample": sample + " per step"},
                 "e2e": {"value": val, "unit": "Gb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "frames_per_s": fps, "air_gbps": fps * n / 1e9}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     import torch
@@ -324,7 +334,7 @@ def main():
         except Exception as e:          # the comparison is a courtesy, never a reason to lose the bench line
             line["reference_gpu_kernel"] = {"unavailable": str(e)[:200]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     dec.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -212,8 +212,8 @@ def default_params(**kw) -> ParamsT:
         if k == "fs_stages":      # ring depth of the staged frame-parallel kernel (A/B experiments)
             p.reserved[4] = (p.reserved[4] & ~255) | int(v)
             continue
-        if k == "fs_nc":          # consumer threads per CTA of the staged kernel: 128 | 256 | 320 (A/B experiments)
-            p.reserved[4] = (p.reserved[4] & 255) | ({128: 1, 256: 2, 320: 3}[int(v)] << 8)
+        if k == "fs_nc":          # consumer threads per CTA of the staged kernel: 128 | 256 (A/B experiments)
+            p.reserved[4] = (p.reserved[4] & 255) | ({128: 1, 256: 2}[int(v)] << 8)
             continue
         if k == "no_pair_fastest":   # keep lane -> (pair t / nrows, row t % nrows) in the static plan (A/B experiments)
             p.reserved[3] = 5 if v else 0

@@ -157,7 +157,7 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
 template <int SEM, int ALGO, int NC, int MAXD>
-__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, NC == 320 ? 2 : (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
+__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];

@@ -117,7 +117,7 @@ def test_dvbs2_long_code_frame_parallel(built, kernel):
     plain frame-parallel kernel (1), bulk-copy-staged kernel (4), and whatever the library picks (0 -> 4)."""
     c = Code.load("64800x32400")
     gg = np.load(GOLD / "k4_64800x32400_x86sse.npz")
-    kw = dict(kernel=4, fs_nc=256) if kernel == 4256 else dict(kernel=kernel)      # 4256: kernel 4 with 256-consumer CTAs
+    kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4000 else dict(kernel=kernel)      # 4256: kernel 4 with 256-consumer CTAs
     r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", **kw)
     assert r["kernel"] == (kw["kernel"] or 4)
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])

@@ -19,6 +19,7 @@ CODE, ITERS, EBN0 = "64800x32400", 10, 2.0
 
 
 def main():
+    out = B.claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=303104)    # 148 SMs x 2 CTAs x 256 consumer threads x 4 frames: every SM carries the same load
     ap.add_argument("--e2e-frames", type=int, default=32768)
@@ -116,7 +117,7 @@ def main():
             line["cpu_baseline"] = {"value": cfps * k_info / 1e9, "unit": "Gb/s", "cores": threads, "kind": "reference", "sample": f"{Fc} frames x {reps} passes ({spent:.1f} s wall on {threads} threads)",
                                     "agrees_with_gpu": bool(np.array_equal(hard, h_hard.array[:Fc]))}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     dece.close()
     if dist is not None: dist.destroy_process_group()
 
