@@ -703,6 +703,11 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     size_t k = h->kernel == 2 ? 1 : h->kernel == 5 ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
+    // frame-parallel kernels: a wave is 300 Ki frames, so the rule above never split a batch and decode() ran H2D, kernel and D2H
+    // back to back.  Quarter the batch over the four stream slots instead (the chunks' kernels share the SMs: a 32 Ki-frame chunk
+    // is 64 CTAs), unless reserved[2] says otherwise.
+    if ((h->kernel == 1 || h->kernel == 4) && h->prm.reserved[2] <= 0 && h->max_frames >= 8192)
+        h->chunk_frames = std::min<size_t>(h->max_frames, (h->max_frames / kSlots + 511) / 512 * 512);
     *out = h;
     return LDPC_OK;
 }

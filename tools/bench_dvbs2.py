@@ -22,7 +22,7 @@ def main():
     out = B.claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=303104)    # 148 SMs x 2 CTAs x 256 consumer threads x 4 frames: every SM carries the same load
-    ap.add_argument("--e2e-frames", type=int, default=32768)
+    ap.add_argument("--e2e-frames", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--kernel", type=int, default=0)
