@@ -48,13 +48,14 @@ __device__ __forceinline__ void oc_vn_one(const GpMode& md, float* V, const floa
     V[n * F + f] = s;
 }
 
+// A thread keeps ONE frame f = tid % F and one task slot = tid / F for the whole decode and walks rows (variables) slot, slot + R,
+// ...: the first version derived (row, frame) from a flat task number with a run-time division per task, and ncu showed the two
+// light phases — variable nodes and stop criterion, 3 to 7 loads per task — spending most of their instructions on that
+// (profiles/r01_ncu_oc_v2.txt: 38 % + 18 % of the kernel's instructions against 36 % for the check-node phase).
 template <bool WRITE_V, bool FLT>
-__device__ __forceinline__ void oc_level(const GpMode& md, float* V, float* MSG, const uint32_t* pos, const OcRow* rows, int r0, int nr, int F, const int* s_done, bool first)
+__device__ __forceinline__ void oc_level(const GpMode& md, float* V, float* MSG, const uint32_t* pos, const OcRow* rows, int r0, int nr, int F, int f, int slot, int R, bool first)
 {
-    const int tasks = nr * F;
-    for (int t = threadIdx.x; t < tasks; t += (int)blockDim.x) {
-        const int ri = t / F, f = t - ri * F;
-        if (s_done[f]) continue;
+    for (int ri = slot; ri < nr; ri += R) {
         const OcRow row = rows[r0 + ri];
 #define OC_CASE(DD) case DD: gp_row<float, DD, WRITE_V, FLT, true>(md, V, MSG, pos, F, f, row.e0, row.cls, first); break;
         switch (row.deg) {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
     extern __shared__ __align__(16) float oc_smem[];
     __shared__ int s_done[OC_MAXF], s_bad[OC_MAXF];
     const int F = A.F, n = A.n, m = A.m, tid = threadIdx.x;
+    const int f = tid % F, slot = tid / F, R = (int)blockDim.x / F;        // this thread's frame and task slot (slot >= R: idle in the task phases)
     float* Vs = oc_smem; float* Ms = Vs + (size_t)n * F; float* Ls = Ms + (size_t)m * F;
     const bool posterior_syndrome = GpIsFloat<S>::value || A.flooding;
 
@@ -89,33 +91,36 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
         int it = 0;
         while (it < A.iters) {
             const bool first = it == 0;
+            const bool live = slot < R && !s_done[f];          // s_done only changes between the barriers at the end of an iteration
             for (int L = 0; L < A.nlevels; L++) {
                 const int r0 = __ldg(A.level_ptr + L), nr = __ldg(A.level_ptr + L + 1) - r0;
-                if (A.flooding) oc_level<false, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
-                else oc_level<true, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, s_done, first);
+                if (live) {
+                    if (A.flooding) oc_level<false, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, f, slot, R, first);
+                    else oc_level<true, GpIsFloat<S>::value>(A.md, Vs, Ms, A.pos, A.rows, r0, nr, F, f, slot, R, first);
+                }
                 __syncthreads();
             }
             if (A.flooding) {
-                for (int t = tid; t < n * F; t += (int)blockDim.x) {
-                    const int nn = t / F, f = t - nn * F;
-                    if (!s_done[f]) oc_vn_one<GpIsFloat<S>::value>(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn);
-                }
+                if (live)
+                    for (int nn = slot; nn < n; nn += R) oc_vn_one<GpIsFloat<S>::value>(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn);
                 __syncthreads();
             }
             it++;
             if (A.et && it < A.iters) {
-                // stop criterion per frame (see gp_syndrome_ok): one task per (row, frame), failures OR-ed into s_bad
-                for (int t = tid; t < A.n_checks * F; t += (int)blockDim.x) {
-                    const int ri = t / F, f = t - ri * F;
-                    if (s_done[f] || s_bad[f]) continue;
-                    const OcRow row = A.rows[ri];
-                    int par = 0;
-                    for (int j = 0; j < row.deg; j++) {
-                        float xx = Vs[(size_t)__ldg(A.pos + row.e0 + j) * F + f];
-                        if (!posterior_syndrome) xx = gp_clamp(xx - Ms[(size_t)(row.e0 + j) * F + f], A.md.lo, A.md.hi);
-                        par ^= (xx > 0.0f);
+                // stop criterion per frame (see gp_syndrome_ok): rows slot, slot + R, ... of frame f; failures OR-ed into s_bad
+                if (live) {
+                    int bad = 0;
+                    for (int ri = slot; ri < A.n_checks && !bad; ri += R) {
+                        const OcRow row = A.rows[ri];
+                        int par = 0;
+                        for (int j = 0; j < row.deg; j++) {
+                            float xx = Vs[__ldg(A.pos + row.e0 + j) * (uint32_t)F + (uint32_t)f];
+                            if (!posterior_syndrome) xx = gp_clamp(xx - Ms[(row.e0 + j) * (uint32_t)F + (uint32_t)f], A.md.lo, A.md.hi);
+                            par ^= (xx > 0.0f);
+                        }
+                        bad = par;
                     }
-                    if (par) s_bad[f] = 1;
+                    if (bad) s_bad[f] = 1;
                 }
                 __syncthreads();
                 int running = 0;

@@ -58,7 +58,7 @@ static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
     // CTA width x widest row body.  The kernel's registers are those of its widest body, and the two producer warps get the same
     // allocation as the consumers: 256 consumers per CTA keep 16 consumer warps on an SM where 128 keep 12.
     // 320 consumers capped at 80 registers (20 consumer warps) were measured 3 % SLOWER at a balanced batch and are not instantiated
-    if (a.nc == 256) { if (a.max_deg <= 8) FS_LAUNCH(256, 8) else FS_LAUNCH(256, FS_MAXDEG) }
+    if (a.nc == 256 && a.max_deg <= 8) FS_LAUNCH(256, 8)        // the degree-10 body needs 120 registers: one wide CTA per SM, never a win
     else             { if (a.max_deg <= 8) FS_LAUNCH(128, 8) else FS_LAUNCH(128, FS_MAXDEG) }
 #undef FS_LAUNCH
     return (int)cudaGetLastError();

@@ -440,7 +440,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     // CTA wins once there are two of them for every SM.  reserved[4] bits 8.. force 128 (1) or 256 (2).
     const size_t fs_words = (t4 + 255) / 256 * 256;
     const int fs_knob = h->prm.reserved[4] >> 8;
-    const int fs_nc = fs_knob == 2 ? 256 : fs_knob == 1 ? FS_CONSUMERS
+    const int fs_nc = h->fs_max_deg > 8 ? FS_CONSUMERS : fs_knob == 2 ? 256 : fs_knob == 1 ? FS_CONSUMERS
                     : (fs_words / 256 >= (size_t)(2 * h->sms * 17 / 20) ? 256 : FS_CONSUMERS);
     const int tq = h->kernel != 4 ? 32 : fs_nc;
     const int T = (int)((t4 + tq - 1) / tq * tq);
