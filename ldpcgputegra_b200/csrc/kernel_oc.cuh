@@ -34,6 +34,7 @@ struct OcArgs {
     const int32_t* level_ptr;   // [nlevels + 1]
     size_t frames;
     int n, m, n_checks, nlevels, F, iters, flooding, et, packed, threads;
+    int packed_syn;          // stop criterion on packed hard-decision words (float or flooding, F <= 32): n words of shared memory behind the state
     GpMode md;
 };
 
@@ -46,6 +47,20 @@ __device__ __forceinline__ void oc_vn_one(const GpMode& md, float* V, const floa
     for (int k = __ldg(cptr + n); k < k1; k++) s = __fadd_rn(s, MSG[__ldg(cedge + k) * F + f]);
     if (!FLT) s = gp_clamp(s, md.lo, md.hi);
     V[n * F + f] = s;
+}
+
+// Hard decisions of F <= 32 frames of one variable as ONE word (bit f = frame f): lanes tid = slot * F + f of a slot are consecutive,
+// so a ballot hands every run of lanes that shares a slot its bits at once; the run's first lane ORs them into hb[nn] (a slot's F
+// frames straddle at most two warps, and two slots never share a word).  Every thread of the CTA must call this (full-mask ballot).
+__device__ __forceinline__ void oc_pack_bits(uint32_t* hb, int nn, bool b, bool mine, int F, int f)
+{
+    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, b);
+    const int lane = (int)(threadIdx.x & 31u);
+    if (mine && (lane == 0 || f == 0)) {
+        const int cnt = min(F - f, 32 - lane);
+        const uint32_t w = ((bits >> lane) & (cnt >= 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u))) << f;
+        if (w) atomicOr(hb + nn, w);
+    }
 }
 
 // A thread keeps ONE frame f = tid % F and one task slot = tid / F for the whole decode and walks rows (variables) slot, slot + R,
@@ -75,6 +90,8 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
     const int f = tid % F, slot = tid / F, R = (int)blockDim.x / F;        // this thread's frame and task slot (slot >= R: idle in the task phases)
     float* Vs = oc_smem; float* Ms = Vs + (size_t)n * F; float* Ls = Ms + (size_t)m * F;
     const bool posterior_syndrome = GpIsFloat<S>::value || A.flooding;
+    uint32_t* const hb = reinterpret_cast<uint32_t*>(Ls + (A.flooding ? (size_t)n * F : 0));     // [n] packed hard decisions (packed_syn only)
+    __shared__ uint32_t s_badw;
 
     for (size_t base = (size_t)blockIdx.x * F; base < A.frames; base += (size_t)gridDim.x * F) {
         const int valid = (int)min((size_t)F, A.frames - base);
@@ -86,6 +103,7 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
             if (A.flooding) Ls[(size_t)nn * F + f] = v;
         }
         if (tid < OC_MAXF) { s_done[tid] = tid < valid ? 0 : 255; s_bad[tid] = 0; }
+        if (A.packed_syn) { for (int i = tid; i < n; i += (int)blockDim.x) hb[i] = 0u; if (tid == 0) s_badw = 0u; }
         if (A.iters == 0 && A.dbg_msgs) for (int i = tid; i < m * F; i += (int)blockDim.x) Ms[i] = 0.0f;
         __syncthreads();
         int it = 0;
@@ -100,15 +118,46 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
                 }
                 __syncthreads();
             }
+            const bool check = A.et && it + 1 < A.iters;          // a stop test follows this iteration
             if (A.flooding) {
-                if (live)
+                if (check && A.packed_syn) {                      // the same pass also packs the new hard decisions (uniform trip count: ballots)
+                    for (int base = 0; base < n; base += R) {
+                        const int nn = base + slot;
+                        const bool mine = slot < R && nn < n;
+                        bool b = false;
+                        if (live && mine) { oc_vn_one<GpIsFloat<S>::value>(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn); b = Vs[(size_t)nn * F + f] > 0.0f; }
+                        oc_pack_bits(hb, nn, b, mine, F, f);
+                    }
+                } else if (live) {
                     for (int nn = slot; nn < n; nn += R) oc_vn_one<GpIsFloat<S>::value>(A.md, Vs, Ms, Ls, A.cptr, A.cedge, F, f, nn);
+                }
+                __syncthreads();
+            } else if (check && A.packed_syn) {
+                for (int base = 0; base < n; base += R) {
+                    const int nn = base + slot;
+                    const bool mine = slot < R && nn < n;
+                    oc_pack_bits(hb, nn, live && mine && Vs[(size_t)nn * F + f] > 0.0f, mine, F, f);
+                }
                 __syncthreads();
             }
             it++;
             if (A.et && it < A.iters) {
-                // stop criterion per frame (see gp_syndrome_ok): rows slot, slot + R, ... of frame f; failures OR-ed into s_bad
-                if (live) {
+                if (A.packed_syn) {
+                    // one task per ROW for all frames at once: XOR of the row's packed words; a set bit = that frame fails the check
+                    uint32_t w = 0u;
+                    for (int ri = tid; ri < A.n_checks; ri += (int)blockDim.x) {
+                        const OcRow row = A.rows[ri];
+                        uint32_t x = 0u;
+                        for (int j = 0; j < row.deg; j++) x ^= hb[__ldg(A.pos + row.e0 + j)];
+                        w |= x;
+                    }
+                    w = __reduce_or_sync(0xFFFFFFFFu, w);
+                    if ((tid & 31) == 0 && w) atomicOr(&s_badw, w);
+                    __syncthreads();
+                    if (tid < F && ((s_badw >> tid) & 1u)) s_bad[tid] = 1;
+                    for (int i = tid; i < n; i += (int)blockDim.x) hb[i] = 0u;       // ready for the next iteration's bits
+                } else if (live) {
+                    // stop criterion per frame (see gp_syndrome_ok): rows slot, slot + R, ... of frame f; failures OR-ed into s_bad
                     int bad = 0;
                     for (int ri = slot; ri < A.n_checks && !bad; ri += R) {
                         const OcRow row = A.rows[ri];
@@ -129,6 +178,7 @@ __global__ void __launch_bounds__(OC_MAX_THREADS, 1) oc_decode_kernel(const __gr
                     running = s_done[tid] == 0;
                     s_bad[tid] = 0;
                 }
+                if (tid == 0) s_badw = 0u;
                 if (!__syncthreads_or(running)) break;
             }
         }

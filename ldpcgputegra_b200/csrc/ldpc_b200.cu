@@ -51,7 +51,7 @@ struct ldpc_b200_handle_s {
     int elem = 1;                   // bytes per LLR / posterior / message element at the boundary (1, 2 or 4)
     GpMode gp_mode{};
     int32_t* d_cptr = nullptr; int32_t* d_cedge = nullptr;
-    OcRow* d_oc_rows = nullptr; int32_t* d_oc_levels = nullptr; int oc_nlevels = 0, oc_F = 0, oc_threads = 0; size_t oc_smem = 0;   // on-chip generic engine (kernel 5)
+    OcRow* d_oc_rows = nullptr; int32_t* d_oc_levels = nullptr; int oc_nlevels = 0, oc_F = 0, oc_threads = 0; size_t oc_smem = 0; bool oc_packed_syn = false;   // on-chip generic engine (kernel 5)
     int levels = 0, sms = 0;
     // row-parallel plan
     int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0, rp_pair_fastest = 0; size_t rp_smem = 0;
@@ -387,7 +387,7 @@ int launch_decode_oc(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t f
     a.pos = h->d_pos; a.cptr = h->d_cptr; a.cedge = h->d_cedge; a.rows = h->d_oc_rows; a.level_ptr = h->d_oc_levels;
     a.frames = frames; a.n = c.n; a.m = c.m; a.n_checks = c.n_checks; a.nlevels = h->oc_nlevels; a.F = h->oc_F; a.iters = iters;
     a.flooding = h->prm.schedule == LDPC_SCHED_FLOODING; a.et = h->prm.early_term == LDPC_ET_SYNDROME;
-    a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.md = h->gp_mode;
+    a.packed = h->prm.out_format == LDPC_OUT_PACKED; a.md = h->gp_mode; a.packed_syn = h->oc_packed_syn ? 1 : 0;
     const int blocks = (int)std::min<size_t>((size_t)h->sms, (frames + h->oc_F - 1) / h->oc_F);
     CU_TRY(h, cudaFuncSetAttribute(oc_decode_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->oc_smem));
     a.threads = h->oc_threads;
@@ -585,7 +585,13 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         // on-chip variant (kernel 5): fp32 state of F frames in shared memory, rows in level order (flooding: one level)
         const bool flooding = params->schedule == LDPC_SCHED_FLOODING;
         const size_t per_frame = (size_t)(code->n + code->m + (flooding ? code->n : 0)) * sizeof(float);
-        const int F = (int)std::min<size_t>(OC_MAXF, ((size_t)prop.sharedMemPerBlockOptin - 1024) / per_frame);
+        // stop criterion on packed hard-decision words (kernel_oc.cuh: oc_pack_bits) where the criterion reads posteriors (float or
+        // flooding): n extra words behind the state, frames-per-CTA <= 32
+        const bool want_syn_words = params->early_term != LDPC_ET_NONE && (params->dtype == LDPC_DTYPE_F32 || flooding);
+        const size_t syn_bytes = want_syn_words ? (size_t)code->n * sizeof(uint32_t) : 0;
+        int F = (int)std::min<size_t>(OC_MAXF, ((size_t)prop.sharedMemPerBlockOptin - 1024 - syn_bytes) / per_frame);
+        if (want_syn_words && F > 32) F = (int)std::min<size_t>(OC_MAXF, ((size_t)prop.sharedMemPerBlockOptin - 1024) / per_frame);   // short codes: the per-frame test
+        h->oc_packed_syn = want_syn_words && F <= 32;
         if (params->kernel == 5 && F < 1) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the on-chip generic engine"); }
         if ((params->kernel == 5 && F >= 1) || (params->kernel == 0 && F >= 8)) {
             std::vector<int32_t> level(code->n_checks, 0);
@@ -605,7 +611,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMemcpy(h->d_oc_rows, rows_sorted.data(), rows_sorted.size() * sizeof(OcRow), cudaMemcpyHostToDevice));
             CREATE_TRY(cudaMalloc((void**)&h->d_oc_levels, level_ptr.size() * sizeof(int32_t)));
             CREATE_TRY(cudaMemcpy(h->d_oc_levels, level_ptr.data(), level_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            h->kernel = 5; h->oc_nlevels = levels; h->oc_F = F; h->oc_smem = per_frame * F;
+            h->kernel = 5; h->oc_nlevels = levels; h->oc_F = F; h->oc_smem = per_frame * F + (h->oc_packed_syn ? syn_bytes : 0);
             // CTA size.  A round of (row, frame) tasks costs max(latency of one task, issue time of the round); the first measurement
             // (T chosen to minimise idle lanes -> 128 threads) was 3x slower than a fixed 512 because short rounds are latency-
             // bound: model a task as ~600 cycles alone and ~2 cycles of issue slots per thread, and minimise the sum over levels.

@@ -142,6 +142,28 @@ def test_staged_kernel_all_semantics(code576, sem, algo):
         pkg.CGPUDecoder(code576, nb_frames=64, device=0, kernel=4, early_term=1)
 
 
+@pytest.mark.parametrize("kernel,name", [(4, "576x288"), (1, "576x288"), (4, "4000x2000")])
+def test_frame_parallel_batch_quartered_over_stream_slots(built, kernel, name):
+    """decode() cuts a frame-parallel batch of >= 8192 frames into four chunks on the four stream slots (the chunks' kernels run
+    concurrently and their copies overlap): same bytes as one chunk (chunk_waves=1), oracle agreement on a sample, a ragged tail,
+    iteration counts, and the packed format."""
+    c = Code.load(name)
+    F = 8192 + 4 * 517 + 3                                           # chunks of 2560 frames, the last one ragged
+    llr = awgn_llr(c, F, 2.0, 901)
+    dec = pkg.CGPUDecoder(c, nb_frames=F, device=0, kernel=kernel, early_term=int(kernel == 1), semantics="ARM_SCALAR" if kernel == 1 else "X86_SSE")
+    hard, it = dec.decode(llr, 10, want_iters=True)
+    one = pkg.CGPUDecoder(c, nb_frames=F, device=0, kernel=kernel, early_term=int(kernel == 1), semantics="ARM_SCALAR" if kernel == 1 else "X86_SSE", chunk_waves=1)
+    hard1, it1 = one.decode(llr, 10, want_iters=True)
+    assert dec.info(pkg.INFO_KERNEL) == kernel and np.array_equal(hard, hard1) and np.array_equal(it, it1)
+    idx = np.r_[0:40, 2540:2580, F - 40:F]                           # across the first chunk boundary and the tail
+    o = oracle_decode(c, dec.params, llr[idx], 10)
+    assert np.array_equal(hard[idx], o["hard"]) and np.array_equal(it[idx], o["iters"])
+    dec.close(); one.close()
+    decp, decb = pkg.CGPUDecoder(c, nb_frames=F, device=0, kernel=kernel, out_format=1), pkg.CGPUDecoder(c, nb_frames=F, device=0, kernel=kernel)
+    assert np.array_equal(decp.decode(llr, 10), oracle_pack(decb.decode(llr, 10), c.n))
+    decp.close(); decb.close()
+
+
 @pytest.mark.parametrize("kernel", [2, 1])
 def test_ragged_sizes_and_packed_output(code576, kernel):
     big = awgn_llr(code576, 700, 1.5, 81)
