@@ -51,6 +51,8 @@ struct FsArgs {
     int rows[LDPC_MAX_DEG_CLASSES];
     int iters, stages, max_deg;
     uint32_t exp_word;       // 0x64646464 (rowops.cuh: bytes01_to_w)
+    uint8_t* iters_done;     // [4*T], nullable
+    int et;                  // per-frame syndrome early termination (the ET instantiation)
     int nc;                  // consumer threads per CTA (128 | 256 | 512): a staged line is nc * 4 bytes.  The bulk-copy engine serves a
                              // request in ~70 cycles whatever its size, so 512-byte lines cap the SM at ~7 B/clk (measured); wider CTAs lift that
     ldpc_params_t prm;
@@ -77,9 +79,9 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // thread's own earlier stores
 // The stage of the PREVIOUS row is handed back here, between this row's arithmetic and its stores: the fence then only has
 // to cover stores that were issued a whole row ago, so it never waits on fresh ones.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC>
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET>
 __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, const uint32_t (&p2)[D], uint32_t stage_s, const RowConsts& K,
-                                       uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool fwd_ok)
+                                       uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool fwd_ok, uint32_t keep_lo, uint32_t keep_hi)
 {
     constexpr uint32_t LINE = NC * 4u;
     uint32_t wv[D], wm[D], nv[D], nm[D];
@@ -112,7 +114,7 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, u
     }
 #pragma unroll
     for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * LINE + 4 * tid);
-    fp_row_math<SEM, ALGO, D, FIRST, false, Q>(wv, wm, K, 0u, 0u, nv, nm);
+    fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);        // ET: frozen frames keep their state
     fence_proxy_async_global();                    // the previous rows' stores, before any later bulk copy of the same lines
     __syncwarp();
     if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
@@ -131,9 +133,9 @@ struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 // global memory (L1 hit for 3 rows out of 4, L2 otherwise) and used to sit at the head of every row's dependency chain
 // (profiles/r01_ncu_fs_v2.txt: 15 % of the stall samples on the long scoreboard).  pos2 is padded by FS_MAXDEG words so that the
 // read past the last row is harmless; the words fetched across a class boundary are simply dropped.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC>
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET>
 __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
-                                         uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c)
+                                         uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c, uint32_t keep_lo, uint32_t keep_hi)
 {
     const uint32_t T4 = 4u * (uint32_t)A.T;
     uint32_t* const vt = A.V + t;
@@ -145,7 +147,7 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
 #pragma unroll
         for (int j = 0; j < D; j++) p2n[j] = __ldg(A.pos2 + e + D + j);
         mbar_wait(bars + 8 * c.stage, c.phase);
-        fs_row<SEM, ALGO, D, FIRST, Q, NC>(A, tid, vt, mp, T4, p2, ring + (uint32_t)c.stage * stage_bytes, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD);
+        fs_row<SEM, ALGO, D, FIRST, Q, NC, ET>(A, tid, vt, mp, T4, p2, ring + (uint32_t)c.stage * stage_bytes, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
         mp = word_at(mp, (uint32_t)D, T4);
         c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
         if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
@@ -154,9 +156,44 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
     }
 }
 
+// Stop criterion, consumer side: one more pass over the row list through the same ring — the producers fetch EVERY line of a row
+// this time (nothing is written, so nothing can be stale once the update pass has drained) — and per row the parity of (x > 0),
+// x = sat(v - m) with the updated messages (ref: code/ldpc_decoder_arm/CDecoder/OMS/CDecoder_OMS_fixed_x86.cpp:150-178; the same
+// words as fp_syndrome in kernel_fp.cuh).  Returns bit15-of-each-half words: 1 = a check of that frame failed.
+template <int NC>
+__device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int lane, const RowConsts& K, int lo, uint32_t bars, uint32_t ring, uint32_t stage_bytes,
+                                                  int Kst, FsCursor& c, uint32_t& bad_lo, uint32_t& bad_hi)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    const h2 inv256 = h2_const(1.0f / 256.0f), half = h2_const(0.5f), lo_np = h2_const((float)(lo - 1) / 256.0f);
+    bad_lo = bad_hi = 0u;
+    for (int cl = 0; cl < A.nb_deg; cl++) {
+        const int D = A.deg[cl];
+        const uint32_t dpar = (D & 1) ? 0x80008000u : 0u;
+        for (int r = 0; r < A.rows[cl]; r++) {
+            mbar_wait(bars + 8 * c.stage, c.phase);
+            const uint32_t st = ring + (uint32_t)c.stage * stage_bytes + 4u * (uint32_t)tid;
+            uint32_t p0 = dpar, p1 = dpar;
+            for (int j = 0; j < D; j++) {
+                const uint32_t wv = lds_u32(st + j * LINE), wm = lds_u32(st + (A.max_deg + j) * LINE);
+                const h2 x0 = __hmin2(__hfma2_sat(bytes01_to_w(wv, K.c64), inv256, __hfma2(bytes01_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
+                const h2 x1 = __hmin2(__hfma2_sat(bytes23_to_w(wv, K.c64), inv256, __hfma2(bytes23_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
+                p0 ^= h2_bits(__hadd2(x0, lo_np));
+                p1 ^= h2_bits(__hadd2(x1, lo_np));
+            }
+            bad_lo |= p0; bad_hi |= p1;
+            __syncwarp();
+            if (lane == 0 && c.prev_empty) mbar_arrive(c.prev_empty);       // same hand-back discipline as the update rows: one row late
+            c.prev_empty = bars + 8 * (Kst + c.stage);
+            if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
+        }
+    }
+    bad_lo &= 0x80008000u; bad_hi &= 0x80008000u;
+}
+
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
-template <int SEM, int ALGO, int NC, int MAXD>
+template <int SEM, int ALGO, int NC, int MAXD, bool ET>
 __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
@@ -181,24 +218,34 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
         const bool msg_side = warp > NC / 32;
         int stage = 0; uint32_t phase = 0;
         const int j = lane & 15;
+        // ET: every iteration but the last is followed by a second pass over the rows for the stop criterion (sweep 1: every line of
+        // every row, hazard flags ignored), each pass behind a CTA barrier so that nothing it reads can be stale
         for (int it = 0; it < A.iters; it++) {
-            size_t e = 0;
-            for (int c = 0; c < A.nb_deg; c++) {
-                const int D = A.deg[c];
-                for (int r = 0; r < A.rows[c]; r++, e += D) {
-                    const uint32_t p2 = (!msg_side && lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : FS_F_HAZARD;     // issued before the wait: the latencies overlap
-                    if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
-                    __syncwarp();
-                    const bool go = msg_side ? (lane < 16 && j < D && it > 0) : !(p2 & FS_F_HAZARD);
-                    const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
-                    const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
-                    if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
-                    __syncwarp();
-                    if (go) {
-                        if (msg_side) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
-                        else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
+            const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
+            for (int sw = 0; sw < sweeps; sw++) {
+                size_t e = 0;
+                for (int c = 0; c < A.nb_deg; c++) {
+                    const int D = A.deg[c];
+                    for (int r = 0; r < A.rows[c]; r++, e += D) {
+                        uint32_t p2 = (!msg_side && lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : FS_F_HAZARD;     // issued before the wait: the latencies overlap
+                        if (sw == 1 && !msg_side && lane < 16 && j < D) p2 &= ~FS_F_HAZARD;
+                        if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
+                        __syncwarp();
+                        const bool go = msg_side ? (lane < 16 && j < D && (it > 0 || sw == 1)) : !(p2 & FS_F_HAZARD);
+                        const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
+                        const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
+                        if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
+                        __syncwarp();
+                        if (go) {
+                            if (msg_side) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                            else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
+                        }
+                        if (++stage == Kst) { stage = 0; phase ^= 1u; }
                     }
-                    if (++stage == Kst) { stage = 0; phase ^= 1u; }
+                }
+                if (ET && sweeps == 2) {
+                    if (sw == 0) __syncthreads();                      // the consumers' stores of this iteration are out (they fenced)
+                    else if (!__syncthreads_or(0)) return;             // every frame of the CTA passed: the consumers leave too
                 }
             }
         }
@@ -209,14 +256,18 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     const int tid = threadIdx.x, t = t0 + tid;
     RowConsts K; make_consts<SEM>(K, A.prm); K.c64 = A.exp_word;
     FsCursor cur{0, 0u, 0u, 0u};
-    for (int it = 0; it < A.iters; it++) {
+    const int lo = (SEM == LDPC_SEM_GPU_FIXED) ? -128 : -A.prm.sat_var;
+    uint32_t keep_lo = 0u, keep_hi = 0u;           // 0xFFFF per half = frame frozen (early-terminated)
+    uint32_t done[4] = { 0u, 0u, 0u, 0u };
+    int it = 0;
+    for (; it < A.iters; it++) {
         size_t e = 0;
         for (int c = 0; c < A.nb_deg; c++) {
             const int D = A.deg[c], R = A.rows[c];
             const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
             // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
             K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
-#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC>(A, tid, t, e, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur)
+#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET>(A, tid, t, e, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
 #define FS_CASE(DD)                                                                          \
     case DD:                                                                                 \
         if constexpr (DD <= MAXD) {                                                          \
@@ -228,6 +279,26 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
 #undef FS_CASE
 #undef FS_GO
         }
+        if (ET && it + 1 < A.iters) {
+            __threadfence();                           // once per iteration: this iteration's stores are performed ...
+            fence_proxy_async_global();                // ... and visible to the producers' bulk copies of the stop-criterion pass
+            __syncthreads();
+            uint32_t b0, b1;
+            fs_syndrome_sweep<NC>(A, tid, lane, K, lo, bars, ring, stage_bytes, Kst, cur, b0, b1);
+            // frames that pass now and were not frozen before stop at iteration it + 1 (same bookkeeping as fp_decode_kernel)
+            const uint32_t pass_lo = ~b0 & 0x80008000u, pass_hi = ~b1 & 0x80008000u;
+            if ((pass_lo & 0x00008000u) && !done[0]) done[0] = it + 1;
+            if ((pass_lo & 0x80000000u) && !done[1]) done[1] = it + 1;
+            if ((pass_hi & 0x00008000u) && !done[2]) done[2] = it + 1;
+            if ((pass_hi & 0x80000000u) && !done[3]) done[3] = it + 1;
+            keep_lo = (done[0] ? 0x0000FFFFu : 0u) | (done[1] ? 0xFFFF0000u : 0u);
+            keep_hi = (done[2] ? 0x0000FFFFu : 0u) | (done[3] ? 0xFFFF0000u : 0u);
+            if (!__syncthreads_or(!(done[0] && done[1] && done[2] && done[3]))) { it++; break; }
+        }
+    }
+    if (A.iters_done) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) A.iters_done[4 * (size_t)t + k] = (uint8_t)((ET && done[k]) ? done[k] : it);
     }
 }
 

@@ -480,8 +480,9 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + fwd_bytes + stages * stage_bytes;
         fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fs_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fs_uniform
                         : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fs_arm : launch_fs_gpu;
+        f.et = et; f.iters_done = d_it4;
         if (iters > 0) CU_TRY(h, (cudaError_t)fn(h->prm.algo, f, ctas, smem, st));
-        if (d_it4) CU_TRY(h, cudaMemsetAsync(d_it4, iters, (size_t)4 * T, st));          // no early termination in this kernel: every frame runs `iters`
+        else if (d_it4) CU_TRY(h, cudaMemsetAsync(d_it4, 0, (size_t)4 * T, st));
     } else {
     fp_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fp_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fp_uniform
                     : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fp_arm : launch_fp_gpu;
@@ -657,13 +658,13 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMemcpy(h->d_edge_of, plan.edge_of.data(), plan.edge_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the row-parallel kernel"); }
     } else if (params->kernel == 2) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "row-parallel kernel needs n <= 16383"); }
-    // frame-parallel family: the staged variant (kernel 4) when the code allows it — no early termination (its producer runs a
-    // fixed row list), degrees 3..8, enough rows for the hazard window to be a small part of an iteration
+    // frame-parallel family: the staged variant (kernel 4) when the code allows it — degrees 3..10, enough rows for the hazard
+    // window to be a small part of an iteration
     if (h->kernel == 1) {
-        bool ok = params->early_term == LDPC_ET_NONE && code->n_checks >= 8 * FS_HAZARD;
+        bool ok = code->n_checks >= 8 * FS_HAZARD;
         int dmax = 0;
         for (int i = 0; i < code->nb_deg; i++) { ok = ok && code->deg[i] >= 3 && code->deg[i] <= FS_MAXDEG && code->n <= (int)FS_IDX_MASK; dmax = std::max(dmax, code->deg[i]); }
-        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs early_term off, row degrees 3..10 and >= 128 rows"); }
+        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs row degrees 3..10 and >= 128 rows"); }
         if (ok && params->kernel != 1) {
             // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
             std::vector<uint32_t> pos2((size_t)code->m + FS_MAXDEG, 0u);      // padded: the consumers fetch one row ahead

@@ -104,6 +104,10 @@ def test_other_codes(built, name):
                 g4 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=4, fs_nc=nc)
                 assert g4["kernel"] == 4
                 assert_same(g4, o, f"{name} {sem}/{algo} kernel 4 NC{nc}")
+            g4e = gpu_decode(c, llr, 12, algo=algo, semantics=sem, kernel=4, early_term=1, want_iters=True)
+            oe = oracle_decode(c, g4e["prm"], llr, 12)
+            assert_same(g4e, oe, f"{name} {sem}/{algo} kernel 4 early termination")
+            assert np.array_equal(g4e["iters"], oe["iters"])
     gold = GOLD / f"k4_{name}_x86sse.npz"
     if gold.exists():
         gg = np.load(gold)
@@ -125,6 +129,25 @@ def test_dvbs2_long_code_frame_parallel(built, kernel):
     assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg["OMS_1_10_sha"])
 
 
+def test_dvbs2_early_termination_staged_vs_plain_vs_oracle(built):
+    """DVB-S2 with the per-frame stop criterion: the staged kernel (a second pass over the ring per iteration), the plain
+    frame-parallel kernel and the CPU restatement agree on hard decisions, posteriors, messages and iteration counts."""
+    c = Code.load("64800x32400")
+    llr = np.concatenate([np.load(GOLD / "k4_64800x32400_x86sse.npz")["llr"][:6], awgn_llr(c, 5, 2.6, 611), awgn_llr(c, 3, 0.5, 612)])
+    res = {}
+    for kernel in (4, 1):
+        res[kernel] = gpu_decode(c, llr, 25, algo="OMS", semantics="ARM_SCALAR", kernel=kernel, early_term=1, want_iters=True)
+        assert res[kernel]["kernel"] == kernel
+    o = oracle_decode(c, res[4]["prm"], llr, 25)
+    for kernel in (4, 1):
+        assert_same(res[kernel], o, f"DVB-S2 early termination kernel {kernel}")
+        assert np.array_equal(res[kernel]["iters"], o["iters"])
+    assert o["iters"].min() < 25 and o["iters"].max() == 25          # some frames stop early, the 0.5 dB ones never do
+    auto = pkg.CGPUDecoder(c, nb_frames=16, device=0, early_term=1)
+    assert auto.info(pkg.INFO_KERNEL) == 4
+    auto.close()
+
+
 @pytest.mark.parametrize("sem,algo", COMBOS)
 def test_staged_kernel_all_semantics(code576, sem, algo):
     """kernel 4 on a batch that spans several CTAs and a ragged tail, every (semantics, algorithm) pair, stage ring depths 2..15"""
@@ -138,8 +161,21 @@ def test_staged_kernel_all_semantics(code576, sem, algo):
         for nc in (128, 256):
             g = gpu_decode(code576, big, 4, algo=algo, semantics=sem, kernel=4, fs_nc=nc)
             assert_same(g, oracle_decode(code576, default_params(algo=algo, semantics=sem), big, 4), f"staged {sem}/{algo} 6 CTAs NC{nc}")
-    with pytest.raises(pkg.LdpcError):
-        pkg.CGPUDecoder(code576, nb_frames=64, device=0, kernel=4, early_term=1)
+    # per-frame early termination in the staged kernel (a second pass over the ring per iteration for the stop criterion): frames of
+    # very different quality in one CTA, iteration counts, frozen state, several ring depths and both CTA widths
+    mixed = np.concatenate([awgn_llr(code576, 300, 4.0, 245), awgn_llr(code576, 250, 0.0, 246), awgn_llr(code576, 477, 2.0, 247), stress_llr(code576, 40, 248, full_range=(sem == "GPU_FIXED"))])
+    for iters, stages, nc in ((10, 0, 128), (20, 2, 128), (7, 0, 256), (2, 9, 256), (3, 15, 128), (1, 0, 128)):
+        g = gpu_decode(code576, mixed, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, early_term=1, want_iters=True)
+        o = oracle_decode(code576, g["prm"], mixed, iters)
+        assert g["kernel"] == 4
+        assert_same(g, o, f"staged ET {sem}/{algo} I{iters} K{stages} NC{nc}")
+        assert np.array_equal(g["iters"], o["iters"]), f"staged ET {sem}/{algo} I{iters}: iteration counts"
+    # all frames of the batch converge early: the CTAs leave the loop long before 50 iterations and say so
+    good = awgn_llr(code576, 1024, 6.0, 249)
+    g = gpu_decode(code576, good, 50, algo=algo, semantics=sem, kernel=4, early_term=1, want_iters=True)
+    o = oracle_decode(code576, g["prm"], good, 50)
+    assert_same(g, o, f"staged ET {sem}/{algo} clean batch")
+    assert np.array_equal(g["iters"], o["iters"]) and g["iters"].max() < 50
 
 
 @pytest.mark.parametrize("kernel,name", [(4, "576x288"), (1, "576x288"), (4, "4000x2000")])
