@@ -114,7 +114,8 @@ typedef struct {
                              5 = generic engine with the state on chip (int16 / float / flooding on short codes) */
     int32_t reserved[5];  /* 0 for production use.  Experiment knobs of this implementation, used by tools/ and the A/B tests only:
                              [0],[1] = (warps, pairs) of an on-chip group; [2] = kernel waves per pipeline chunk of decode();
-                             [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping; [4] = stage-ring depth */
+                             [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping;
+                             [4] = stage-ring depth of the staged kernel (bits 0..7) | its CTA width (bits 8..: 1 = 128, 2 = 256 consumer threads) */
 } ldpc_params_t;
 
 typedef struct ldpc_b200_handle_s* ldpc_handle;
