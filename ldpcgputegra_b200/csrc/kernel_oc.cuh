@@ -16,7 +16,7 @@
 
 namespace ldpcb200 {
 
-#define OC_MAX_THREADS 576          // the host picks the CTA size that wastes the fewest lanes over the levels (multiple of 32)
+#define OC_MAX_THREADS 1024         // the host picks the CTA size that needs the fewest rounds per iteration (multiple of 32); 64 registers x 1024 fit one SM
 #define OC_MAXF 64
 
 struct OcRow { uint32_t e0; uint16_t deg; uint16_t cls; };

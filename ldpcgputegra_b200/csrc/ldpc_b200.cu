@@ -613,17 +613,18 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMalloc((void**)&h->d_oc_levels, level_ptr.size() * sizeof(int32_t)));
             CREATE_TRY(cudaMemcpy(h->d_oc_levels, level_ptr.data(), level_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
             h->kernel = 5; h->oc_nlevels = levels; h->oc_F = F; h->oc_smem = per_frame * F + (h->oc_packed_syn ? syn_bytes : 0);
-            // CTA size.  A round of (row, frame) tasks costs max(latency of one task, issue time of the round); the first measurement
-            // (T chosen to minimise idle lanes -> 128 threads) was 3x slower than a fixed 512 because short rounds are latency-
-            // bound: model a task as ~600 cycles alone and ~2 cycles of issue slots per thread, and minimise the sum over levels.
-            auto round_cost = [](long tasks) { return std::max(600.0, 2.0 * (double)tasks); };
-            double best_cost = 1e300;
+            // CTA size.  A thread owns (frame, slot): a level of nr rows takes ceil(nr / R) rounds, R = T / F slots, and a round is
+            // latency-bound (one task is a ~600-cycle dependency chain, the CTA's warps overlap theirs).  So: the fewest rounds per
+            // iteration, then the fewest threads that achieve them.  (Two earlier models — fewest idle lanes, and a latency/issue sum
+            // that is flat in T — picked 128 and 320 threads and were 3x and 1.5x slower than the widest CTA.)
+            long best_rounds = -1;
             for (int T = 128; T <= OC_MAX_THREADS; T += 32) {
-                double cost = 0;
-                auto add = [&](long tasks) { cost += (double)(tasks / T) * round_cost(T) + (tasks % T ? round_cost(tasks % T) : 0.0); };
-                for (int L = 0; L < levels; L++) add((long)(level_ptr[L + 1] - level_ptr[L]) * F);
-                if (flooding) add((long)code->n * F);
-                if (cost < best_cost) { best_cost = cost; h->oc_threads = T; }
+                const long R = T / F;
+                if (R < 1) continue;
+                long rounds = 0;
+                for (int L = 0; L < levels; L++) rounds += ((long)(level_ptr[L + 1] - level_ptr[L]) + R - 1) / R;
+                if (flooding) rounds += ((long)code->n + R - 1) / R;
+                if (best_rounds < 0 || rounds < best_rounds) { best_rounds = rounds; h->oc_threads = T; }
             }
         }
     }
