@@ -2,12 +2,12 @@
 //
 // Same mapping and arithmetic as kernel_fp.cuh (one thread = 4 frames, rows strictly in reference order: the only legal
 // mapping for DVB-S2 64800x32400, whose reference order is a 32 399-deep chain — SURVEY App. C), but the loads no longer sit
-// on the threads' critical path: a producer warp walks the row list K rows ahead of the consumers and pulls every row's
-// posterior lines V[idx][t0..t0+127] and message lines MSG[e][t0..t0+127] (512 contiguous bytes each) into a K-stage ring with
-// cp.async.bulk (TMA, non-tensor form) completing on an mbarrier per stage; consumers read their word from the stage, do the
-// row, store the results straight to HBM, and hand the stage back.  Memory-level parallelism is then K rows x 14 lines x 512 B
-// per CTA whatever the number of resident threads — the frame-parallel kernel needs ~60 K resident threads (256 Ki frames) to
-// pull 55 % of HBM bandwidth, this one is meant to get there with a 64 Ki-frame batch.
+// on the threads' critical path: two producer warps (posterior lines / message lines) walk the row list K rows ahead of the
+// consumers and pull every row's posterior lines V[idx][t0..t0+NC-1] and message lines MSG[e][t0..t0+NC-1] (NC*4 contiguous bytes
+// each, NC = 128 | 256 consumer threads) into a K-stage ring with cp.async.bulk (TMA, non-tensor form) completing on an mbarrier
+// per stage; consumers read their word from the stage, do the row, store the results straight to HBM, and hand the stage back.
+// Memory-level parallelism is then K rows x 14 lines x NC*4 B per CTA whatever the number of resident threads.  Measured
+// (DESIGN.md 3.2b): DVB-S2 20.5 Gb/s = 0.89 of the measured HBM peak on algorithmic bytes at a batch that fills every SM alike.
 // (The reference re-reads both arrays through a per-row __syncthreads pair: code/gpu_fixed/decoder_oms/cuda/CUDA_OMS_SIMD.cu:141-187.)
 //
 // Staleness.  A line prefetched for row q was read up to K rows early, so it is wrong if one of the K rows before q wrote the
@@ -19,13 +19,16 @@
 // 910 ns per DVB-S2 row, all of it this load), so the last FS_FWD rows' outputs are also kept in a small per-thread ring in
 // shared memory and flagged edges whose writer is that close read the ring instead (pos2 bits 30..26: forward, rows back - 1,
 // edge slot of the writer).  Messages are private to their edge and a whole iteration old when they are fetched.
+// The common pattern — one forwardable hazard edge per row — is summarised per row (FS_ROW_SHIFT) and served by copying the ring word
+// into the stage slot.  Early termination (template parameter ET) adds a second, read-only pass over the ring per iteration for the
+// per-frame stop criterion (fs_syndrome_sweep) and a CTA-wide exit.
 // Roofline: HBM, 4*M bytes per frame-iteration as for kernel_fp.
 #pragma once
 #include "kernel_fp.cuh"
 
 namespace ldpcb200 {
 
-#define FS_CONSUMERS 128                 // granularity of the state arrays' row pitch (words); a CTA has NC = 128, 256 or 512 consumer threads + 2 producer warps
+#define FS_CONSUMERS 128                 // the narrow CTA; a CTA has NC = 128 or 256 consumer threads + 2 producer warps, the state arrays' row pitch is a multiple of NC words
 #define FS_PRODUCER_THREADS 64           // one warp fetches the posterior lines, one the message lines: a bulk copy costs ~46 issue cycles, and
                                          // the single producer of the first version (1340 cycles per row) bounded small batches
 #define FS_MAX_CONSUMERS 512
@@ -45,7 +48,7 @@ namespace ldpcb200 {
 struct FsArgs {
     uint32_t* V;
     uint32_t* MSG;
-    const uint32_t* pos2;    // [m] variable index | hazard << 31
+    const uint32_t* pos2;    // [m + FS_MAXDEG] variable index | hazard flags | row summary (see the FS_* masks)
     int T, n, m, nb_deg;
     int deg[LDPC_MAX_DEG_CLASSES];
     int rows[LDPC_MAX_DEG_CLASSES];
@@ -53,8 +56,7 @@ struct FsArgs {
     uint32_t exp_word;       // 0x64646464 (rowops.cuh: bytes01_to_w)
     uint8_t* iters_done;     // [4*T], nullable
     int et;                  // per-frame syndrome early termination (the ET instantiation)
-    int nc;                  // consumer threads per CTA (128 | 256 | 512): a staged line is nc * 4 bytes.  The bulk-copy engine serves a
-                             // request in ~70 cycles whatever its size, so 512-byte lines cap the SM at ~7 B/clk (measured); wider CTAs lift that
+    int nc;                  // consumer threads per CTA (128 | 256): a staged line is nc * 4 bytes
     ldpc_params_t prm;
 };
 
