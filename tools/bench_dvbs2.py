@@ -97,7 +97,8 @@ def main():
                        "parallelism": f"frame-sharded x{world}, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": bytes_per_frame, "algorithmic_bytes_per_launch": F * bytes_per_frame,
-                         "note": "N in + N out + I*4*M (posterior and message read+write per edge, 1 B each); the SM-issue roof coincides for this code (SURVEY 8d)"},
+                         "note": "N in + N out + I*4*M (posterior and message read+write per edge, 1 B each); the SM-issue roof coincides for this code (SURVEY 8d); "
+                                 "traffic: a 10-iteration launch was not captured — profiles/r01_ncu_fs_v3.txt (2 iterations, same batch) measured 442 GB of DRAM traffic = 0.85 x the algorithmic bytes of those two iterations"},
             "e2e": {"value": e2e_fps * k_info / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": Fe * n, "d2h_bytes_per_step": Fe * n, "frames_per_step": Fe,
                     "api": "ldpc_b200_decode (blocking, pinned host buffers)"},
             "gpu_launches": int(launches), "kernel": {1: "frame-parallel (HBM state)", 4: "frame-parallel, bulk-copy staged (cp.async.bulk + mbarrier ring)"}.get(kernel, str(kernel)),
