@@ -353,6 +353,16 @@ def test_dvbs2_full_batch_properties(built):
     assert np.array_equal(dec.decode(llr[perm], 10), hard[perm])
     assert hard.any()                                               # 1 dB is below this code's waterfall at 10 iterations: real work, not all-zero output
     dec.close()
+    # the same with the per-frame stop criterion near the waterfall (frames stop at very different iterations inside one CTA):
+    # staged == plain on every frame, iteration counts included
+    e4, e1 = pkg.CGPUDecoder(c, nb_frames=4096, early_term=1), pkg.CGPUDecoder(c, nb_frames=4096, early_term=1, kernel=1)
+    assert e4.info(pkg.INFO_KERNEL) == 4
+    llr2 = np.concatenate([llr[:2048], e4.awgn(2048, pkg.sigma_for(1.8, 0.5), seed=32)])
+    h4, it4 = e4.decode(llr2, 30, want_iters=True)
+    h1, it1 = e1.decode(llr2, 30, want_iters=True)
+    assert np.array_equal(h4, h1) and np.array_equal(it4, it1)
+    assert it4.max() == 30 and (it4 < 30).sum() > 500
+    e4.close(); e1.close()
 
 
 def test_argument_errors_return_codes_not_exits(code576):
