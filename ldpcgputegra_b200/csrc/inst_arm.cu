@@ -20,12 +20,5 @@ int launch_rp_arm(int algo, int et, const RpArgs& args, int blocks, int threads,
     return (int)cudaErrorInvalidValue;
 }
 
-int launch_fs_arm(int algo, const FsArgs& args, int blocks, size_t smem, cudaStream_t st)
-{
-    switch (algo) {
-    case LDPC_ALGO_OMS: return do_fs<LDPC_SEM_ARM_SCALAR, LDPC_ALGO_OMS>(args, blocks, smem, st);
-    }
-    return (int)cudaErrorInvalidValue;
-}
 
 }  // namespace ldpcb200

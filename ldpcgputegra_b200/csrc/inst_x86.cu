@@ -24,14 +24,5 @@ int launch_rp_x86(int algo, int et, const RpArgs& args, int blocks, int threads,
     return (int)cudaErrorInvalidValue;
 }
 
-int launch_fs_x86(int algo, const FsArgs& args, int blocks, size_t smem, cudaStream_t st)
-{
-    switch (algo) {
-    case LDPC_ALGO_OMS: return do_fs<LDPC_SEM_X86_SSE, LDPC_ALGO_OMS>(args, blocks, smem, st);
-    case LDPC_ALGO_NMS:
-    case LDPC_ALGO_2NMS: return do_fs<LDPC_SEM_X86_SSE, LDPC_ALGO_NMS>(args, blocks, smem, st);
-    }
-    return (int)cudaErrorInvalidValue;
-}
 
 }  // namespace ldpcb200
