@@ -66,7 +66,7 @@ static void* worker(void* arg)
         const double t0 = now_s();
         int rc;
         if (s->real_encoder) {      /* random information bits -> systematic codeword -> BPSK + AWGN (ref: -encoder, main_p.cpp:232-233, GenericEncoder.cpp:38-78) */
-            rc = ldpc_b200_encode_device(w->enc, NULL, w->d_cw, s->frames, s->seed * 7919u + (uint64_t)w->point, first, NULL);
+            rc = ldpc_b200_encode_device(w->enc, NULL, w->d_cw, s->frames, s->seed * 7919u + (uint64_t)w->point, first, ldpc_b200_stream(w->h, 0));   /* one stream for the whole batch: NULL below = the same slot-0 stream */
             if (!rc) rc = ldpc_b200_awgn_codeword_device(w->h, w->d_llr, w->d_cw, s->frames, w->sigma, s->seed + (uint64_t)w->point, first, NULL);
         } else rc = ldpc_b200_awgn_device(w->h, w->d_llr, s->frames, w->sigma, s->seed + (uint64_t)w->point, first, NULL);
         if (!rc) rc = ldpc_b200_decode_device(w->h, w->d_llr, w->d_hard, s->frames, s->iters, NULL, NULL);

@@ -176,8 +176,16 @@ int  ldpc_b200_host_free(void* p);
 int  ldpc_b200_device_alloc(ldpc_handle h, void** p, size_t bytes);
 int  ldpc_b200_device_free(ldpc_handle h, void* p);
 
-/* decode with DEVICE buffers on a caller-supplied CUDA stream (cudaStream_t passed as void*; NULL = handle's slot-0 stream).
- * This is what `value` in bench.py times.  d_iters_done nullable. */
+/* CUDA streams across this ABI are cudaStream_t passed as void*.  For every entry point that takes a HANDLE, NULL means the
+ * handle's slot-0 stream (a non-blocking stream: it is NOT ordered against the legacy default stream).  ldpc_b200_stream returns
+ * a slot's stream so that a C host can put calls that take no handle (ldpc_b200_encode_device) on the same stream. */
+void* ldpc_b200_stream(ldpc_handle h, int slot);
+
+/* decode with DEVICE buffers on a caller-supplied CUDA stream (NULL = handle's slot-0 stream).
+ * This is what `value` in bench.py times.  d_iters_done nullable.  The call works in the scratch state of slot 0 (frame-parallel
+ * and generic kernels: posteriors, messages, iteration counts): consecutive calls on DIFFERENT streams, or a call followed by
+ * decode()/decode_async(slot 0), are ordered one behind the other by an event (they never overlap); the caller's own buffers
+ * are the caller's to order. */
 int  ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t frames, int iters,
                              uint8_t* d_iters_done, void* cuda_stream);
 
@@ -208,7 +216,9 @@ const char* ldpc_b200_encoder_last_error(ldpc_encoder e);      /* nullable: last
 int  ldpc_b200_encoder_info(ldpc_encoder e, int* n_phases, int* dense_unknowns);
 int  ldpc_b200_encode(ldpc_encoder e, const uint8_t* info /*[frames][n - n_checks]*/, uint8_t* codeword /*[frames][n]*/, size_t frames);   /* host buffers */
 /* device buffers; d_info nullable = counter-based random information bits of (seed, first_frame), first_frame % 32 == 0
- * (ref: rand()%2 in GenericEncoder.cpp:47-51) */
+ * (ref: rand()%2 in GenericEncoder.cpp:47-51).  The encoder has no handle, so here cuda_stream == NULL is the legacy default
+ * stream AND the call returns only when the codeword is complete (a decoder handle's streams are non-blocking streams that the
+ * default stream does not order); to pipeline, pass an explicit stream — ldpc_b200_stream(h, 0) puts it on the decoder's. */
 int  ldpc_b200_encode_device(ldpc_encoder e, const uint8_t* d_info, uint8_t* d_codeword, size_t frames, uint64_t seed, uint64_t first_frame, void* cuda_stream);
 /* channel and counters for a transmitted codeword: BPSK 0 -> -1, 1 -> +1 (ref: CChanelAWGN_MKL.cpp:129-139), same noise stream as
  * ldpc_b200_awgn_device for the same (seed, frame); errors counted against the codeword over the information part

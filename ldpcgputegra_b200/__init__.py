@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "ldpc_b200_device_alloc": (i32, [vp, C.POINTER(vp), sz]),
         "ldpc_b200_device_free": (i32, [vp, vp]),
         "ldpc_b200_decode_device": (i32, [vp, vp, vp, sz, i32, vp, vp]),
+        "ldpc_b200_stream": (vp, [vp, i32]),
         "ldpc_b200_set_debug": (i32, [vp, i32]),
         "ldpc_b200_debug_state": (i32, [vp, vp, vp, sz]),
         "ldpc_b200_awgn_device": (i32, [vp, vp, sz, C.c_float, u64, u64, vp]),
@@ -123,7 +124,7 @@ EXPORTS = ["ldpc_b200_abi_version", "ldpc_b200_device_count", "ldpc_b200_status_
            "ldpc_b200_load_code_header", "ldpc_b200_load_code_table", "ldpc_b200_save_code_table", "ldpc_b200_check_code",
            "ldpc_b200_free_code", "ldpc_b200_level_schedule", "ldpc_b200_create", "ldpc_b200_destroy", "ldpc_b200_last_error",
            "ldpc_b200_get_info", "ldpc_b200_quantize", "ldpc_b200_decode", "ldpc_b200_decode_async", "ldpc_b200_sync",
-           "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
+           "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_stream", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
            "ldpc_b200_awgn_device", "ldpc_b200_awgn", "ldpc_b200_count_errors_device",
            "ldpc_b200_encoder_create", "ldpc_b200_encoder_destroy", "ldpc_b200_encoder_last_error", "ldpc_b200_encoder_info", "ldpc_b200_encode",
            "ldpc_b200_encode_device", "ldpc_b200_awgn_codeword_device", "ldpc_b200_count_errors_ref_device"]
@@ -262,6 +263,7 @@ class CGPUDecoder:
         self.params = params if params is not None else default_params(**kw)
         self._h = C.c_void_p()
         self.np_dtype = NP_DTYPE.get(self.params.dtype, np.int8)     # element type of LLRs / posteriors / messages at the boundary
+        self._inflight = {}                                          # slot -> arrays an asynchronous decode still reads / writes
         c = code.c_struct()
         _check(lib().ldpc_b200_create(C.byref(self._h), C.byref(c), C.byref(self.params), device, nb_frames))
 
@@ -294,11 +296,23 @@ class CGPUDecoder:
         _check(lib().ldpc_b200_quantize(self._h, y.ctypes.data, q.ctypes.data, y.size), self._h)
         return q
 
+    def _check_io(self, llr: np.ndarray, out: np.ndarray | None):
+        """Shapes, dtypes and layout the C side takes on trust (it only sees pointers)."""
+        if llr.size % self.code.n or (llr.ndim == 2 and llr.shape[1] != self.code.n):
+            raise LdpcError(ERR_INVALID, f"llr must be [frames, {self.code.n}], got {llr.shape}")
+        frames = llr.size // self.code.n
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous or not out.flags.writeable:
+                raise LdpcError(ERR_INVALID, "out must be a writable C-contiguous uint8 array")
+            if out.nbytes < frames * self.hard_row_bytes:
+                raise LdpcError(ERR_INVALID, f"out holds {out.nbytes} bytes, {frames} frames need {frames * self.hard_row_bytes}")
+        return frames
+
     def decode(self, llr: np.ndarray, iterations: int, out: np.ndarray | None = None, want_iters: bool = False):
         """llr: [frames, n] (host) of the handle's dtype (int8 / int16 / float32).  Returns hard decisions [frames, n] bytes in
         {0,1} (or packed), optionally iteration counts."""
         llr = np.ascontiguousarray(llr, dtype=self.np_dtype)
-        frames = llr.shape[0] if llr.ndim == 2 else llr.size // self.code.n
+        frames = self._check_io(llr, out)
         if out is None:
             out = np.empty((frames, self.hard_row_bytes), dtype=np.uint8)
         it = np.empty(frames, dtype=np.uint8) if want_iters else None
@@ -306,13 +320,27 @@ class CGPUDecoder:
         return (out, it) if want_iters else out
 
     def decode_async(self, slot: int, llr: np.ndarray, out: np.ndarray, iterations: int):
-        frames = llr.shape[0]
+        """Asynchronous: the copies run after this returns.  The (possibly converted) input and the output are kept alive on the
+        object until sync(slot); pass pinned arrays (PinnedArray) for the copies to overlap."""
+        llr = np.ascontiguousarray(llr, dtype=self.np_dtype)
+        frames = self._check_io(llr, out)
+        if out is None:
+            raise LdpcError(ERR_INVALID, "decode_async needs an output array")
         _check(lib().ldpc_b200_decode_async(self._h, slot, llr.ctypes.data, out.ctypes.data, frames, iterations, None), self._h)
+        self._inflight.setdefault(slot, []).append((llr, out))
 
     decode_stream = decode_async  # ref: CGPUDecoder::decode_stream
 
     def sync(self, slot: int = -1):
         _check(lib().ldpc_b200_sync(self._h, slot), self._h)
+        if slot < 0:
+            self._inflight.clear()
+        else:
+            self._inflight.pop(slot, None)
+
+    def stream(self, slot: int = 0) -> int:
+        """cudaStream_t of a stream slot as an integer (ldpc_b200_stream)."""
+        return int(lib().ldpc_b200_stream(self._h, slot) or 0)
 
     def decode_device(self, d_llr: int, d_hard: int, frames: int, iterations: int, d_iters: int = 0, stream: int = 0):
         _check(lib().ldpc_b200_decode_device(self._h, d_llr, d_hard, frames, iterations, d_iters or None, stream or None), self._h)

@@ -340,6 +340,9 @@ int ldpc_b200_encode_device(ldpc_encoder e, const uint8_t* d_info, uint8_t* d_co
     const unsigned g4 = (unsigned)std::min<size_t>((frames * (size_t)e->n + 255) / 256, 1u << 18);
     enc_unpack_kernel<<<g4, 256, 0, st>>>(e->d_words, d_codeword, frames, e->n, W);
     ENC_TRY(cudaGetLastError());
+    // NULL = legacy default stream, which the decoder handles' non-blocking streams are not ordered against: finish before returning,
+    // so that a following ldpc_b200_awgn_codeword_device(..., NULL) (slot-0 stream of its handle) reads a complete codeword
+    if (!st) ENC_TRY(cudaStreamSynchronize(st));
     return LDPC_OK;
 }
 

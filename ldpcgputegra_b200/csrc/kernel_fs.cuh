@@ -76,6 +76,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // generic-proxy global writes -> visible to later async-proxy (bulk copy) reads.  The .global form is a bare FENCE.VIEW.ASYNC.G;
 // the unqualified form costs a MEMBAR.ALL.GPU on top (cuobjdump)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// generic-proxy shared-memory writes -> ordered before later async-proxy (bulk copy) writes of the same stage slot
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one row for the consumer: words come from the stage unless the edge is flagged (hazard) — then from global, after this
 // thread's own earlier stores
@@ -99,6 +101,11 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, u
             const uint32_t ws = (p2[1] >> FS_ROW_SHIFT) & 15u, back = ((p2[2] >> FS_ROW_SHIFT) & 3u) + 1u;
             const uint32_t v = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * (uint32_t)A.max_deg + ws) * NC + tid) * 4u);
             sts_u32(stage_s + hs * LINE + 4 * tid, v);        // read back below by this same thread: program order
+            // The slot is overwritten by a bulk copy (async proxy) once the stage has been handed back, one row from now.  PTX orders a
+            // generic-proxy access before a later async-proxy access of the same shared location only through a proxy fence of that state
+            // space (memory consistency model, "proxy fence": fence.proxy.async[.shared::cta]) followed by the release/acquire chain this
+            // thread -> __syncwarp -> lane 0's mbarrier.arrive (release.cta) -> producer's try_wait (acquire.cta) -> cp.async.bulk.
+            fence_proxy_async_shared();
         } else generic = true;
     }
 #pragma unroll

@@ -38,6 +38,9 @@ struct Slot {
     uint32_t* d_MSG = nullptr;   size_t msg_bytes = 0;
     uint8_t* d_LLR0 = nullptr;   size_t llr0_bytes = 0;    // generic engine, flooding: interleaved channel values
     int T = 0;                                              // words per variable the V/MSG buffers were laid out for
+    // The slot's scratch (d_V, d_MSG, d_LLR0, d_iters) may be used from a caller's stream (decode_device) as well as from the slot's
+    // own: `busy` is recorded behind every use and a use from ANOTHER stream waits on it first.
+    cudaEvent_t busy = nullptr; cudaStream_t last = nullptr; bool used = false;
 };
 
 }  // namespace
@@ -62,6 +65,7 @@ struct ldpc_b200_handle_s {
     bool debug = false;
     int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_post_bytes = 0, dbg_msgs_bytes = 0, dbg_frames = 0; int dbg_iters = 0;
     unsigned long long* d_counters = nullptr;
+    float* d_qy = nullptr; int8_t* d_qq = nullptr; size_t qy_bytes = 0, qq_bytes = 0;     // scratch of ldpc_b200_quantize, grown on demand, kept
     int64_t launches = 0;
     std::string err;
 };
@@ -314,9 +318,11 @@ void destroy_impl(ldpc_handle h)
     cudaSetDevice(h->device);
     for (auto& s : h->slot) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        if (s.busy) cudaEventDestroy(s.busy);
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
     cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2);
+    cudaFree(h->d_qy); cudaFree(h->d_qq);
     cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge); cudaFree(h->d_oc_rows); cudaFree(h->d_oc_levels);
     free(h->code.pos);
     delete h;
@@ -332,6 +338,43 @@ int ensure_debug(ldpc_handle h, size_t frames, int iters)
 }
 
 size_t hard_row_bytes(ldpc_handle h) { return h->prm.out_format == LDPC_OUT_PACKED ? (size_t)(h->code.n + 7) / 8 : (size_t)h->code.n; }
+
+// A slot's scratch is about to be used on stream st: order it behind the slot's previous use when that ran on another stream.
+int slot_enter(ldpc_handle h, Slot& s, cudaStream_t st)
+{
+    if (s.used && s.last != st) CU_TRY(h, cudaStreamWaitEvent(st, s.busy, 0));
+    return LDPC_OK;
+}
+int slot_leave(ldpc_handle h, Slot& s, cudaStream_t st)
+{
+    CU_TRY(h, cudaEventRecord(s.busy, st));
+    s.used = true; s.last = st;
+    return LDPC_OK;
+}
+
+// device buffers of one slot for `frames` frames through decode_async: allocated (or grown) BEFORE a pipeline starts, so that no
+// cudaFree / cudaMalloc — both device-wide synchronisation points — lands between the asynchronous copies and kernels of other slots
+int reserve_slot(ldpc_handle h, Slot& s, size_t frames, bool want_iters)
+{
+    const ldpc_code_t& c = h->code;
+    const size_t el = (size_t)h->elem;
+    int rc;
+    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * (size_t)c.n * el))) return rc;
+    if ((rc = ensure(h, &s.d_hard, &s.hard_bytes, frames * hard_row_bytes(h)))) return rc;
+    if (h->kernel == 3) {
+        const size_t T = (frames + 31) / 32 * 32;
+        if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * el))) return rc;
+        if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * el))) return rc;
+        if (h->prm.schedule == LDPC_SCHED_FLOODING && (rc = ensure(h, &s.d_LLR0, &s.llr0_bytes, (size_t)c.n * T * el))) return rc;
+        if (want_iters && (rc = ensure(h, &s.d_iters, &s.iters_bytes, T))) return rc;
+    } else if (h->kernel == 1 || h->kernel == 4) {
+        const size_t tq = h->kernel == 4 ? FS_MAX_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq;       // the widest row pitch launch_decode may pick
+        if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
+        if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
+        if (want_iters && (rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc;
+    } else if (want_iters && (rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc;
+    return LDPC_OK;
+}
 
 // generic engine: interleave (+ clamp) -> decode -> hard decisions; S = storage type of the boundary and of the HBM state
 template <class S>
@@ -449,7 +492,10 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
     s.T = T;
     dim3 tg((unsigned)((frames + 127) / 128), (unsigned)((c.n + 127) / 128));
-    interleave_kernel<<<tg, 256, 0, st>>>(d_llr, s.d_V, frames, c.n, T, lo, hi);
+    // the way in covers every word of the row pitch T (the staged kernel rounds T up to its CTA width and runs all T threads): padding
+    // frames get zero LLRs — an all-zero, syndrome-passing frame — instead of whatever the allocation held
+    dim3 tgi((unsigned)((T + 31) / 32), tg.y);
+    interleave_kernel<<<tgi, 256, 0, st>>>(d_llr, s.d_V, frames, c.n, T, lo, hi);
     CU_TRY(h, cudaGetLastError());
     FpArgs a{};
     a.V = s.d_V; a.MSG = s.d_MSG; a.pos = h->d_pos; a.iters_done = nullptr; a.T = T; a.n = c.n; a.m = c.m; a.nb_deg = c.nb_deg;
@@ -562,7 +608,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     cudaDeviceProp prop;
     CREATE_TRY(cudaGetDeviceProperties(&prop, device));
     h->sms = prop.multiProcessorCount;
-    for (auto& s : h->slot) CREATE_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto& s : h->slot) { CREATE_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); CREATE_TRY(cudaEventCreateWithFlags(&s.busy, cudaEventDisableTiming)); }
     CREATE_TRY(cudaMalloc((void**)&h->d_pos, sizeof(uint32_t) * (size_t)code->m));
     CREATE_TRY(cudaMemcpy(h->d_pos, code->pos, sizeof(uint32_t) * (size_t)code->m, cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc((void**)&h->d_counters, 2 * sizeof(unsigned long long)));
@@ -738,6 +784,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     return LDPC_OK;
 }
 
+void* ldpc_b200_stream(ldpc_handle h, int slot) { return (h && slot >= 0 && slot < kSlots) ? (void*)h->slot[slot].stream : nullptr; }
+
 int ldpc_b200_set_debug(ldpc_handle h, int enable) { if (!h) return LDPC_ERR_INVALID; h->debug = enable != 0; return LDPC_OK; }
 
 int ldpc_b200_host_alloc(void** p, size_t bytes)
@@ -771,8 +819,11 @@ int ldpc_b200_decode_device(ldpc_handle h, const void* d_llr, uint8_t* d_hard, s
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->slot[0].stream;
     const bool dbg = h->debug;
-    if (dbg) { int rc; if ((rc = ensure_debug(h, frames, iters))) return rc; }
-    return launch_decode(h, h->slot[0], (const int8_t*)d_llr, d_hard, frames, iters, d_iters_done, st, dbg);
+    int rc;
+    if (dbg && (rc = ensure_debug(h, frames, iters))) return rc;
+    if ((rc = slot_enter(h, h->slot[0], st))) return rc;
+    if ((rc = launch_decode(h, h->slot[0], (const int8_t*)d_llr, d_hard, frames, iters, d_iters_done, st, dbg))) return rc;
+    return slot_leave(h, h->slot[0], st);
 }
 
 int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* hard, size_t frames, int iters, uint8_t* iters_done)
@@ -784,21 +835,18 @@ int ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* ha
     Slot& s = h->slot[slot];
     const size_t n = h->code.n, hb = hard_row_bytes(h), el = (size_t)h->elem;
     int rc;
-    if ((rc = ensure(h, &s.d_llr, &s.llr_bytes, frames * n * el))) return rc;
-    if ((rc = ensure(h, &s.d_hard, &s.hard_bytes, frames * hb))) return rc;
-    uint8_t* d_it = nullptr;
-    if (iters_done) {
-        if (h->kernel == 2 || h->kernel == 5) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, frames))) return rc; d_it = s.d_iters; }
-        else if (h->kernel == 3) { if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, (frames + 31) / 32 * 32))) return rc; d_it = s.d_iters; }
-        else { const size_t tq = h->kernel == 4 ? FS_MAX_CONSUMERS : 32, T = ((frames + 3) / 4 + tq - 1) / tq * tq; if ((rc = ensure(h, &s.d_iters, &s.iters_bytes, 4 * T))) return rc; d_it = s.d_iters; }
-    }
+    // a no-op when decode() reserved the slots up front; a direct caller with growing batches pays the (device-synchronising)
+    // reallocation here
+    if ((rc = reserve_slot(h, s, frames, iters_done != nullptr))) return rc;
+    uint8_t* const d_it = iters_done ? s.d_iters : nullptr;
+    if ((rc = slot_enter(h, s, s.stream))) return rc;
     CU_TRY(h, cudaMemcpyAsync(s.d_llr, llr, frames * n * el, cudaMemcpyHostToDevice, s.stream));
     const bool dbg = h->debug && slot == 0;
     if (dbg && (rc = ensure_debug(h, frames, iters))) return rc;
     if ((rc = launch_decode(h, s, s.d_llr, s.d_hard, frames, iters, d_it, s.stream, dbg))) return rc;
     CU_TRY(h, cudaMemcpyAsync(hard, s.d_hard, frames * hb, cudaMemcpyDeviceToHost, s.stream));
     if (iters_done) CU_TRY(h, cudaMemcpyAsync(iters_done, d_it, frames, cudaMemcpyDeviceToHost, s.stream));
-    return LDPC_OK;
+    return slot_leave(h, s, s.stream);
 }
 
 int ldpc_b200_sync(ldpc_handle h, int slot)
@@ -815,6 +863,13 @@ int ldpc_b200_decode(ldpc_handle h, const void* llr, uint8_t* hard, size_t frame
     const size_t n = h->code.n, hb = hard_row_bytes(h);
     const size_t chunk = (h->debug) ? std::max<size_t>(frames, 1) : h->chunk_frames;   // debug: one chunk so the state is whole
     int rc = LDPC_OK, k = 0;
+    if (frames == 0) return LDPC_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    {   // size the slots this call will use BEFORE anything asynchronous is queued: the first chunk is the largest
+        const size_t nchunks = (frames + chunk - 1) / chunk, first = std::min(chunk, frames);
+        for (int s = 0; s < kSlots && (size_t)s < nchunks && !h->debug; s++)
+            if ((rc = reserve_slot(h, h->slot[s], first, iters_done != nullptr))) return rc;
+    }
     for (size_t f = 0; f < frames && rc == LDPC_OK; f += chunk, k++) {
         const size_t cnt = std::min(chunk, frames - f);
         const int slot = h->debug ? 0 : (k % kSlots);
@@ -841,16 +896,15 @@ int ldpc_b200_quantize(ldpc_handle h, const float* y, int8_t* q, size_t count)
     if (!h || !y || !q) return fail(h, LDPC_ERR_INVALID, "quantize: bad argument");
     if (count == 0) return LDPC_OK;
     CU_TRY(h, cudaSetDevice(h->device));
-    float* d_y = nullptr; int8_t* d_q = nullptr;
-    CU_TRY(h, cudaMalloc((void**)&d_y, count * sizeof(float)));
-    cudaError_t e = cudaMalloc((void**)&d_q, count);
-    if (e != cudaSuccess) { cudaFree(d_y); return fail(h, LDPC_ERR_CUDA, cudaGetErrorString(e)); }
+    int rc;
+    if ((rc = ensure(h, &h->d_qy, &h->qy_bytes, count * sizeof(float)))) return rc;       // scratch lives on the handle: no cudaMalloc / cudaFree per call
+    if ((rc = ensure(h, &h->d_qq, &h->qq_bytes, count))) return rc;
     cudaStream_t st = h->slot[0].stream;
-    cudaMemcpyAsync(d_y, y, count * sizeof(float), cudaMemcpyHostToDevice, st);
-    quantize_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 65535), 256, 0, st>>>(d_y, d_q, count, (float)h->prm.llr_scale, h->prm.sat_llr);
-    cudaMemcpyAsync(q, d_q, count, cudaMemcpyDeviceToHost, st);
-    e = cudaStreamSynchronize(st);
-    cudaFree(d_y); cudaFree(d_q);
+    CU_TRY(h, cudaMemcpyAsync(h->d_qy, y, count * sizeof(float), cudaMemcpyHostToDevice, st));
+    quantize_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 65535), 256, 0, st>>>(h->d_qy, h->d_qq, count, (float)h->prm.llr_scale, h->prm.sat_llr);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(q, h->d_qq, count, cudaMemcpyDeviceToHost, st));
+    const cudaError_t e = cudaStreamSynchronize(st);
     h->launches += 1;
     if (e != cudaSuccess) return fail(h, LDPC_ERR_CUDA, cudaGetErrorString(e));
     return LDPC_OK;

@@ -104,6 +104,30 @@ def oracle_pack(hard: np.ndarray, n: int):
     return out
 
 
+# ---- code tables and parameters WITHOUT the product library (bench.py --impl reference must not map libldpc_b200.so) --------
+def read_ldpc_table(name_or_path) -> Code:
+    """Pure-Python reader of this repo's .ldpc table files (layout: ldpcgputegra_b200/csrc/code_table.cpp, save_code_table):
+    8-byte magic, int32 {n, n_checks, m, nb_deg, deg[8], rows[8], index_bytes}, then m indices of 2 or 4 bytes."""
+    p = Path(name_or_path)
+    if not p.exists():
+        p = ROOT / "ldpcgputegra_b200" / "codes" / f"{name_or_path}.ldpc"
+    raw = p.read_bytes()
+    hdr = np.frombuffer(raw, np.int32, 4 + 2 * 8 + 1, offset=8)
+    n, n_checks, m, nb_deg = (int(x) for x in hdr[:4])
+    ib = int(hdr[20])
+    pos = np.frombuffer(raw, np.uint16 if ib == 2 else np.uint32, m, offset=8 + 4 * 21).astype(np.uint32)
+    return Code(n, n_checks, [int(x) for x in hdr[4:4 + nb_deg]], [int(x) for x in hdr[12:12 + nb_deg]], pos)
+
+
+def reference_default_params() -> ParamsT:
+    """ldpc_b200_default_params restated in Python (ref: code/x86/main_p.cpp:90-104,133-139) for callers that must not load the product."""
+    p = ParamsT()
+    p.algo, p.schedule, p.dtype, p.semantics = ALGO["OMS"], 0, 0, SEM["X86_SSE"]
+    p.offset, p.factor_q5, p.factor1, p.factor2 = 1, 29, 0.75, 0.875
+    p.sat_var, p.sat_msg, p.llr_scale, p.sat_llr = 127, 31, 8, 31
+    return p
+
+
 # ---- the reference's own decoders, compiled from /root/reference into oracle/_ref (optional) -----------------------
 def ref_x86(code_name: str):
     p = REF_DIR / f"libref_x86_{code_name}.so"

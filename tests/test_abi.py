@@ -1,6 +1,7 @@
 """CPU suite, part 2: the drop-in boundary without a GPU — the library loads, exports every symbol include/ldpc_b200.h declares,
 the H-matrix loader / level schedule work, and compute entry points fail loudly instead of falling back to a CPU path."""
 import ctypes as C
+from pathlib import Path
 import re
 
 import numpy as np
@@ -121,3 +122,46 @@ def test_encoder_analysis_runs_on_the_host(built):
             with pytest.raises(pkg.LdpcError) as e:
                 pkg.Encoder(pkg.Code.load(name))
             assert e.value.status == pkg.ERR_NO_DEVICE
+
+
+REF = Path("/root/reference/code")
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present on this machine")
+def test_header_parser_on_the_real_reference_headers(built):
+    """The H-matrix loader run over the reference's own headers where they lie — every x86-tree table (one file) and every gpu_fixed
+    table (macros + index array in two files) — against the bundled .ldpc tables minted from them and the level counts of SURVEY App. C."""
+    x86 = {"576x288": "576x288", "1944x972": "1944x972", "2048x384": "2048x384", "2304x1152": "2304x1152", "4000x2000": "4000x2000",
+           "64800x32400": "64800x32400.dvb-s2", "64800x7200": "64800x7200.dvb-s2", "64800x6480": "64800x6480.dvb-s2"}
+    seen = 0
+    for name, d in x86.items():
+        c = pkg.Code.from_header(REF / "x86/Constantes" / d / "constantes_sse.h")
+        b = pkg.Code.load(name)
+        assert (c.n, c.n_checks, c.m, c.deg, c.rows) == (b.n, b.n_checks, b.m, b.deg, b.rows) and np.array_equal(c.pos, b.pos), name
+        assert sum(dg * r for dg, r in zip(c.deg, c.rows)) == c.m and sum(c.rows) == c.n_checks and int(c.pos.max()) < c.n
+        seen += 1
+    for d in sorted(p for p in (REF / "gpu_fixed/matrix").iterdir() if p.is_dir()):
+        if not (d / "constantes_decoder.h").exists():
+            continue
+        g = pkg.Code.from_header(d / "constantes_gpu.h", d / "constantes_decoder.h")
+        b = pkg.Code.load(d.name)
+        assert (g.n, g.n_checks, g.deg, g.rows) == (b.n, b.n_checks, b.deg, b.rows) and np.array_equal(g.pos, b.pos), d.name
+        seen += 1
+    assert seen >= 20
+    for name, levels in (("576x288", 10), ("2304x1152", 10), ("1200x600", 464), ("64800x32400", 32399)):
+        assert pkg.Code.load(name).level_schedule()[0] == levels, name
+
+
+def test_reference_arm_of_the_bench_runs_without_the_product_library(built, tmp_path):
+    """`bench.py --impl reference` times the reference's CPU decoder and must not even map libldpc_b200.so: run it with the library
+    path pointed at nothing (any use of the product would raise) and look at the process's own list of mapped objects."""
+    import json, os, subprocess, sys
+    env = dict(os.environ, LDPC_B200_LIB=str(tmp_path / "absent.so"), LDPC_BENCH_REPORT_MAPS="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--frames", "2048"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert not any("libldpc_b200" in m for m in line["mapped_objects"]), line["mapped_objects"]
+    assert any("oracle" in m for m in line["mapped_objects"])

@@ -88,3 +88,36 @@ def test_c_simulator_real_encoder(built):
     assert "systematic, derived from H" in out and "all-zero codeword" in out0
     fe, fe0 = pts[2.0]["fe"], pts0[2.0]["fe"]
     assert 0.04 < pts[2.0]["fer"] < 0.062 and abs(fe - fe0) <= 4.0 * (fe + fe0) ** 0.5, (fe, fe0)
+
+
+def test_c_simulator_real_encoder_many_batches(built, code576):
+    """-encoder over MANY small batches: encoder, channel, decoder and counters of consecutive batches run on one stream (the encoder
+    has no handle: the harness passes it the decoder's slot-0 stream).  A batch whose channel read a half-written or a previous
+    batch's codeword would count about half of its bits as errors; the FER must stay at the all-zero-codeword value instead."""
+    out, pts = run_sim("-fixed", "-sse", "-OMS", 1, "-iter", 10, "-min", 2.5, "-max", 2.5, "-fer", 100000, "-frames", 512, "-max-frames", 131072, "-encoder")
+    out0, pts0 = run_sim("-fixed", "-sse", "-OMS", 1, "-iter", 10, "-min", 2.5, "-max", 2.5, "-fer", 100000, "-frames", 512, "-max-frames", 131072)
+    assert pts[2.5]["frames"] == 131072 and pts0[2.5]["frames"] == 131072             # 256 batches each
+    fe, fe0 = pts[2.5]["fe"], pts0[2.5]["fe"]
+    assert fe0 > 50 and abs(fe - fe0) <= 5.0 * (fe + fe0) ** 0.5, (fe, fe0)
+    assert pts[2.5]["ber"] < 3 * pts0[2.5]["ber"] + 1e-6
+
+
+def test_encoder_null_stream_is_safe_without_synchronisation(built, code576):
+    """ldpc_b200_encode_device(..., stream NULL) followed at once by awgn_codeword_device(..., NULL): NULL means the legacy default
+    stream for the handle-less encoder and the handle's non-blocking slot-0 stream for the channel, which nothing orders — the
+    encoder therefore finishes before it returns.  Checked by decoding noiseless codewords of many consecutive batches."""
+    import torch
+    enc = pkg.Encoder(code576, device=0)
+    F = 4096
+    dec = pkg.CGPUDecoder(code576, nb_frames=F, device=0)
+    d_cw = torch.empty((F, code576.n), dtype=torch.uint8, device="cuda")
+    d_llr = torch.empty((F, code576.n), dtype=torch.int8, device="cuda")
+    d_hard = torch.empty((F, code576.n), dtype=torch.uint8, device="cuda")
+    for b in range(24):
+        enc.encode_device(d_cw.data_ptr(), F, seed=5, first_frame=b * F)              # stream 0 = NULL
+        dec.awgn_codeword_device(d_llr.data_ptr(), d_cw.data_ptr(), F, 0.05, seed=9, first_frame=b * F)   # NULL = slot-0 stream
+        dec.decode_device(d_llr.data_ptr(), d_hard.data_ptr(), F, 3)
+        be, fe = dec.count_errors_ref_device(d_hard.data_ptr(), d_cw.data_ptr(), F)
+        assert (be, fe) == (0, 0), f"batch {b}: {be} bit errors at sigma 0.05"
+        assert int(d_cw.sum().item()) > F * code576.n // 4                              # random codewords, not the all-zero word
+    dec.close(); enc.close()

@@ -35,7 +35,7 @@ def test_k123_x86sse_576(code576):
                 assert [sha(o["post"]), sha(o["msgs"])] == list(g[key + "_sha"]), key
 
 
-@pytest.mark.parametrize("name", ["1944x972", "2048x384", "2304x1152", "4000x2000", "64800x32400"])
+@pytest.mark.parametrize("name", ["1944x972", "2048x384", "2304x1152", "4000x2000", "64800x32400", "64800x7200", "64800x6480"])
 def test_k4_other_codes(built, name):
     c = Code.load(name)
     g = np.load(GOLD / f"k4_{name}_x86sse.npz")

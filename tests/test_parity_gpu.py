@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 
 import ldpcgputegra_b200 as pkg
-from _helpers import (Code, default_params, oracle_decode, oracle_quantize, oracle_pack, awgn_llr, stress_llr, ROOT,
-                      ref_gpu, ref_gpu_decode)
+from _helpers import (Code, default_params, oracle_decode, oracle_decode_mt, oracle_quantize, oracle_pack, awgn_llr, stress_llr, ROOT,
+                      ref_gpu, ref_gpu_decode, ref_x86, ALGO)
 
 pytestmark = pytest.mark.gpu
 GOLD = ROOT / "tests" / "golden"
@@ -127,6 +127,29 @@ def test_dvbs2_long_code_frame_parallel(built, kernel):
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
     import hashlib
     assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg["OMS_1_10_sha"])
+
+
+@pytest.mark.parametrize("name", ["64800x7200", "64800x6480"])
+def test_dvbs2_high_rate_tables(built, name):
+    """The reference tree's other two DVB-S2 tables (rate 8/9: rows of degree 27/26; rate 9/10: 30/29 — code/x86/Constantes/
+    64800x7200.dvb-s2, 64800x6480.dvb-s2) against fixtures minted from the reference's own x86 decoder: OMS and NMS, hard decisions,
+    SHA-256 of posteriors and messages, through whatever kernel the library picks and through the plain frame-parallel kernel."""
+    import hashlib
+    c = Code.load(name)
+    gg = np.load(GOLD / f"k4_{name}_x86sse.npz")
+    for algo, param in (("OMS", 1), ("NMS", 29)):
+        key = f"{algo}_{param}_10"
+        for kernel in (0, 1):
+            r = gpu_decode(c, gg["llr"], 10, algo=algo, semantics="X86_SSE", offset=param, factor_q5=param, kernel=kernel)
+            assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg[key + "_hard"]), (key, kernel)
+            assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg[key + "_sha"]), (key, kernel, r["kernel"])
+    # GPU_FIXED semantics and early termination on the same table against the CPU restatement (a handful of frames: the oracle is scalar)
+    llr = gg["llr"][4:10]
+    for kw in (dict(algo="OMS", semantics="GPU_FIXED"), dict(algo="OMS", semantics="ARM_SCALAR", early_term=1)):
+        g = gpu_decode(c, llr, 12, want_iters=True, **kw)
+        o = oracle_decode(c, g["prm"], llr, 12)
+        assert_same(g, o, f"{name} {kw}")
+        assert np.array_equal(g["iters"], o["iters"])
 
 
 def test_dvbs2_early_termination_staged_vs_plain_vs_oracle(built):
@@ -255,6 +278,74 @@ def test_full_batch_properties_64k(code576):
     conv = np.flatnonzero(~hard.any(axis=1))[:4096]
     again = dec.decode(np.where(hard[conv] > 0, 31, -31).astype(np.int8), 10)
     assert not again.any()
+    dec.close()
+
+
+def test_full_batch_every_frame_against_the_reference_decoder(code576):
+    """BASELINE configs[1] at full size, EVERY frame: all 65 536 hard-decision rows of the GPU (on-chip kernel through the blocking
+    host call, and the device-resident entry point) equal the reference's own x86 SSE decoder run on all host threads
+    (oracle/_ref, CDecoder_OMS_fixed_SSE) — or the C restatement when the reference binary was not built here."""
+    import os
+    F = 65536
+    dec = pkg.CGPUDecoder(code576, nb_frames=F)
+    llr = dec.awgn(F, pkg.sigma_for(2.0, 0.5), seed=2024)
+    hard = dec.decode(llr, 10)
+    threads = len(os.sched_getaffinity(0))
+    L = ref_x86("576x288")
+    if L is not None:
+        ref = np.empty((F, code576.n), np.uint8)
+        assert L.ref_x86_decode_mt(ALGO["OMS"], 1, llr.ctypes.data, ref.ctypes.data, F, 10, threads) >= 0
+    else:
+        ref = oracle_decode_mt(code576, dec.params, llr, 10, threads)
+    assert np.array_equal(hard, ref), f"{(hard != ref).any(axis=1).sum()} of {F} frames differ from the reference decoder"
+    for algo, param in (("NMS", 29),):
+        d2 = pkg.CGPUDecoder(code576, nb_frames=F, algo=algo, factor_q5=param)
+        h2 = d2.decode(llr, 10)
+        if L is not None:
+            assert L.ref_x86_decode_mt(ALGO[algo], param, llr.ctypes.data, ref.ctypes.data, F, 10, threads) >= 0
+        else:
+            ref = oracle_decode_mt(code576, d2.params, llr, 10, threads)
+        assert np.array_equal(h2, ref), f"{algo}: {(h2 != ref).any(axis=1).sum()} frames differ"
+        d2.close()
+    dec.close()
+
+
+def test_python_layer_validates_shapes(code576):
+    """The C side only sees pointers: the binding refuses arrays whose shape, dtype or layout would make it read or write out of bounds."""
+    dec = pkg.CGPUDecoder(code576, nb_frames=64)
+    llr = awgn_llr(code576, 8, 2.0, 1)
+    for bad_llr in (llr[:, :288], np.zeros((3, 100), np.int8)):
+        with pytest.raises(pkg.LdpcError):
+            dec.decode(bad_llr, 2)
+    for bad_out in (np.empty((4, 576), np.uint8), np.empty((8, 576), np.int8), np.empty((8, 1152), np.uint8)[:, ::2]):     # too small, wrong dtype, strided
+        with pytest.raises(pkg.LdpcError):
+            dec.decode(llr, 2, out=bad_out)
+    out = np.empty((8, 576), np.uint8)
+    assert dec.decode(llr, 2, out=out) is out
+    dec.close()
+
+
+def test_decode_device_on_two_streams_shares_slot_scratch_safely(built):
+    """decode_device works in slot 0's scratch state (frame-parallel kernels): calls issued on two different streams without any
+    synchronisation in between must still produce what they produce one after the other."""
+    import torch
+    c = Code.load("4000x2000")
+    F = 8192
+    dec = pkg.CGPUDecoder(c, nb_frames=F, kernel=4)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    d_llr = [torch.empty((F, c.n), dtype=torch.int8, device="cuda") for _ in range(2)]
+    d_hard = [torch.empty((F, c.n), dtype=torch.uint8, device="cuda") for _ in range(4)]
+    dec.awgn_device(d_llr[0].data_ptr(), F, pkg.sigma_for(2.0, 0.5), 11, 0, sa.cuda_stream)
+    dec.awgn_device(d_llr[1].data_ptr(), F, pkg.sigma_for(1.0, 0.5), 12, 0, sa.cuda_stream)
+    torch.cuda.synchronize()
+    for k in range(2):                                   # reference: one call at a time
+        dec.decode_device(d_llr[k].data_ptr(), d_hard[k].data_ptr(), F, 10, stream=sa.cuda_stream)
+        torch.cuda.synchronize()
+    for rep in range(3):                                 # back to back on two streams, no host synchronisation
+        dec.decode_device(d_llr[0].data_ptr(), d_hard[2].data_ptr(), F, 10, stream=sa.cuda_stream)
+        dec.decode_device(d_llr[1].data_ptr(), d_hard[3].data_ptr(), F, 10, stream=sb.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_hard[0], d_hard[2]) and torch.equal(d_hard[1], d_hard[3])
     dec.close()
 
 

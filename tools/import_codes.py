@@ -14,7 +14,7 @@ from ldpcgputegra_b200 import Code, CODES_DIR
 
 REF = Path("/root/reference/code")
 X86 = {"576x288": "576x288", "1944x972": "1944x972", "2048x384": "2048x384", "2304x1152": "2304x1152", "4000x2000": "4000x2000",
-       "64800x32400": "64800x32400.dvb-s2"}
+       "64800x32400": "64800x32400.dvb-s2", "64800x7200": "64800x7200.dvb-s2", "64800x6480": "64800x6480.dvb-s2"}
 
 
 def load_gpu(d: Path):
