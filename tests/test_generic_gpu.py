@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import ldpcgputegra_b200 as pkg
-from _helpers import Code, oracle_decode, oracle_decode_float, awgn_llr, stress_llr
+from _helpers import Code, oracle_decode, oracle_decode_float, awgn_llr, stress_llr, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +63,26 @@ def test_int8_flooding(code576, sem, algo, kernel):
         g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, schedule="FLOODING", early_term=et, kernel=kernel)
         assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"flooding {sem}/{algo}/I{iters}/et{et}/k{kernel}")
     assert g["iters"].min() < 30
+
+
+@pytest.mark.parametrize("kernel", ENGINES)
+def test_int16_pinned_against_the_reference_scalar_decoder(code576, kernel):
+    """K7: the int16 storage path against the only reference code with wider-than-int8 state — the ARM tree's scalar decoder at
+    rails far beyond int8 (fixture minted from it by tools/gen_golden.py: setVarRange(+-2047)/setMsgRange(+-511), +-32767/+-8191,
+    +-300/+-300; posteriors reach the rails, messages 8188): hard decisions, posteriors, messages and iteration counts, both generic
+    engines (kernel 3: HBM state, kernel 5: on-chip state)."""
+    g7 = np.load(ROOT / "tests" / "golden" / "k7_576x288_armscalar_wide.npz")
+    llr = g7["llr"].astype(np.int16)
+    seen_wide = False
+    for key in [k[:-5] for k in g7.files if k.endswith("_hard")]:
+        _, off, sv, sm, imax, early = key.split("_")
+        g = gpu_decode(code576, llr, int(imax), dtype="I16", semantics="ARM_SCALAR", algo="OMS", offset=int(off), sat_var=int(sv), sat_msg=int(sm),
+                       early_term=int(early), kernel=kernel)
+        assert np.array_equal(np.packbits(g["hard"], axis=1, bitorder="little"), g7[key + "_hard"]), key
+        assert np.array_equal(g["post"], g7[key + "_post"]) and np.array_equal(g["msgs"], g7[key + "_msgs"]), key
+        assert np.array_equal(g["iters"], g7[key + "_iters"]), key
+        seen_wide = seen_wide or int(np.abs(g["post"].astype(np.int32)).max()) > 127
+    assert seen_wide
 
 
 @pytest.mark.parametrize("kernel", ENGINES)

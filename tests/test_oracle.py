@@ -60,6 +60,35 @@ def test_k5_arm_scalar_early_termination(code576):
     assert g["ET_1_127_31_30_iters"].min() < 30   # the fixture does exercise early stops
 
 
+def test_k7_int16_wide_rails_against_the_arm_scalar_reference(code576):
+    """int16 storage is pinned by the ARM tree's scalar decoder (short arrays, run-time rails) at rails beyond int8: fixture K7."""
+    g = np.load(GOLD / "k7_576x288_armscalar_wide.npz")
+    llr = g["llr"].astype(np.int16)
+    keys = [k[:-5] for k in g.files if k.endswith("_hard")]
+    assert len(keys) == 6
+    for key in keys:
+        _, off, sv, sm, imax, early = key.split("_")
+        prm = default_params(algo="OMS", semantics="ARM_SCALAR", dtype=1, offset=int(off), sat_var=int(sv), sat_msg=int(sm), early_term=int(early))
+        o = oracle_decode(code576, prm, llr, int(imax))
+        assert np.array_equal(o["hard"], unpack(g[key + "_hard"], code576.n)), key
+        assert np.array_equal(o["post"], g[key + "_post"]) and np.array_equal(o["msgs"], g[key + "_msgs"]) and np.array_equal(o["iters"], g[key + "_iters"]), key
+    assert int(np.abs(g["W_3_32767_8191_30_0_post"].astype(np.int32)).max()) == 32767 and int(np.abs(g["W_3_32767_8191_30_0_msgs"].astype(np.int32)).max()) > 8000
+    assert g["W_1_2047_511_20_1_iters"].min() < 20
+
+
+def test_live_reference_arm_wide_rails(code576):
+    L = ref_arm("576x288")
+    if L is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    llr = np.clip(5 * awgn_llr(code576, 40, 2.5, 17).astype(np.int16), -128, 127).astype(np.int8)
+    for off, sv, sm, early in ((2, 4095, 1023, True), (1, 32767, 32767, False)):
+        prm = default_params(algo="OMS", semantics="ARM_SCALAR", dtype=1, offset=off, sat_var=sv, sat_msg=sm, early_term=int(early))
+        r = ref_arm_decode(L, code576, off, sv, sm, early, llr, 25)
+        o = oracle_decode(code576, prm, llr.astype(np.int16), 25)
+        assert np.array_equal(r["iters"], o["iters"]) and np.array_equal(r["hard"], o["hard"])
+        assert np.array_equal(r["post"], o["post"]) and np.array_equal(r["msgs"], o["msgs"])
+
+
 def test_live_reference_x86(code576):
     L = ref_x86("576x288")
     if L is None:

@@ -5,6 +5,7 @@ The reference ships no golden vectors, so the fixtures under tests/
   K1/K2/K3  576x288  x86 SSE binary: OMS offset 1/2, NMS factor 29/24, I in {1,2,5,10}, AWGN @2 dB + saturating stress inputs
   K4        16 frames each of 1944x972, 2048x384, 2304x1152, 4000x2000, 64800x32400, I=10 (posteriors/messages as SHA-256 for the big ones)
   K5        ARM-tree scalar decoder with the stop criterion: per-frame iteration counts, I_max in {10,30}, 1..3 dB
+  K7        ARM-tree scalar decoder at rails beyond int8 (+-2047/+-511, +-32767/+-8191, +-300/+-300): pins the int16 storage path
 Run in the container that has /root/reference; the GPU box and CI only read the .npz files.
 """
 import hashlib
@@ -43,8 +44,35 @@ def mint_k4(names):
         np.savez_compressed(OUT / f"k4_{name}_x86sse.npz", **out)
 
 
+def mint_k7():
+    """K7: int16 storage.  The only reference code with wider-than-int8 state is the ARM tree's scalar decoder (short arrays, run-time
+    rails: code/ldpc_decoder_arm/CDecoder/template/CDecoder_fixed_x86.h:29-30, OMS/CDecoder_OMS_fixed_x86.cpp:30-32,61-200).  Rails far
+    beyond int8 — setVarRange(+-2047) / setMsgRange(+-511) and +-32767 / +-8191 — full-range int8 inputs (its decode() takes signed
+    char), 20 and 30 iterations so that posteriors and messages leave [-127, 127]; with and without the stop criterion."""
+    code = Code.load("576x288")
+    La = ref_arm("576x288")
+    assert La is not None, "oracle/_ref/libref_arm_576x288.so missing (make -C oracle ref)"
+    llr = np.concatenate([4 * awgn_llr(code, 24, 2.0, 701).astype(np.int16), 4 * awgn_llr(code, 16, 3.5, 702).astype(np.int16),
+                          stress_llr(code, 16, 703, full_range=True).astype(np.int16), 3 * awgn_llr(code, 8, 0.5, 704).astype(np.int16)])
+    llr = np.clip(llr, -128, 127).astype(np.int8)
+    out = {"llr": llr}
+    for (off, sv, sm) in [(1, 2047, 511), (3, 32767, 8191), (0, 300, 300)]:
+        for imax, early in [(20, True), (30, False)]:
+            r = ref_arm_decode(La, code, off, sv, sm, early, llr, imax)
+            key = f"W_{off}_{sv}_{sm}_{imax}_{int(early)}"
+            out[key + "_hard"] = np.packbits(r["hard"], axis=1, bitorder="little")
+            out[key + "_iters"] = r["iters"]
+            out[key + "_post"] = r["post"]; out[key + "_msgs"] = r["msgs"]
+            print(key, "max |posterior|", int(np.abs(r["post"].astype(np.int32)).max()), "max |message|", int(np.abs(r["msgs"].astype(np.int32)).max()),
+                  "iterations", int(r["iters"].min()), "..", int(r["iters"].max()))
+    np.savez_compressed(OUT / "k7_576x288_armscalar_wide.npz", **out)
+
+
 def main():
     OUT.mkdir(exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "k7":
+        mint_k7()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "k4":      # mint only the named K4 fixtures (leaves the committed ones untouched)
         mint_k4(sys.argv[2:])
         return
@@ -77,6 +105,7 @@ def main():
             out[key + "_iters"] = r["iters"]
             out[key + "_post"] = r["post"].astype(np.int8); out[key + "_msgs"] = r["msgs"].astype(np.int8)
     np.savez_compressed(OUT / "k5_576x288_armscalar_et.npz", **out)
+    mint_k7()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)
 
