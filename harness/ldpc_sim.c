@@ -209,7 +209,7 @@ int main(int argc, char** argv)
     }
     int64_t kern = 0; ldpc_b200_get_info(w[0].h, LDPC_INFO_KERNEL, &kern);
     printf("(II) ENCODER              : %s\n", sim.real_encoder ? "systematic, derived from H (random information bits)" : "all-zero codeword (CFakeEncoder)");
-    printf("(II) DECODE KERNEL        : %s\n", kern == 2 ? "row-parallel, on-chip state" : kern == 3 ? "generic engine (fp32 arithmetic, HBM state)" : kern == 5 ? "generic engine (fp32 arithmetic, on-chip state)" : kern == 4 ? "frame-parallel, bulk-copy staged" : "frame-parallel, HBM state");
+    printf("(II) DECODE KERNEL        : %s\n", kern == 2 ? "row-parallel, on-chip state" : kern == 3 ? "generic engine (fp32 arithmetic, HBM state)" : kern == 5 ? "generic engine (fp32 arithmetic, on-chip state)" : kern == 6 ? "generic engine (fp32 arithmetic, on-chip state, warp per frame)" : kern == 4 ? "frame-parallel, bulk-copy staged" : "frame-parallel, HBM state");
 
     const double t_simu = now_s();
     int point = 0;

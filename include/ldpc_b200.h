@@ -111,7 +111,9 @@ typedef struct {
     int32_t kernel;       /* 0 = auto; 1 = frame-parallel (HBM-resident state); 2 = row-parallel on-chip (short codes);
                              3 = generic engine (fp32 arithmetic: int16 / float / flooding, and int8 layered as a cross-check);
                              4 = frame-parallel with the state staged through shared memory by cp.async.bulk (long codes);
-                             5 = generic engine with the state on chip (int16 / float / flooding on short codes) */
+                             5 = generic engine with the state on chip, a CTA owns F frames (int16 / float / flooding on short codes);
+                             6 = generic engine with the state on chip, ONE WARP PER FRAME and a global work queue (the same modes; chosen
+                                 when >= 8 frames fit per SM and the schedule fills the lanes: flooding, or layered with wide levels) */
     int32_t reserved[5];  /* 0 for production use.  Experiment knobs of this implementation, used by tools/ and the A/B tests only:
                              [0],[1] = (warps, pairs) of an on-chip group; [2] = kernel waves per pipeline chunk of decode();
                              [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping;
@@ -145,7 +147,7 @@ int  ldpc_b200_create(ldpc_handle* h, const ldpc_code_t* code, const ldpc_params
 void ldpc_b200_destroy(ldpc_handle h);                          /* ref: CGPUDecoder::~CGPUDecoder CGPUDecoder.cpp:41-54 */
 const char* ldpc_b200_last_error(ldpc_handle h);                /* nullable handle: last create() error of this thread  */
 int  ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value);
-enum { LDPC_INFO_KERNEL = 0,            /* which decode kernel the handle selected (1 .. 5)                        */
+enum { LDPC_INFO_KERNEL = 0,            /* which decode kernel the handle selected (1 .. 6)                        */
        LDPC_INFO_LEVELS = 1,            /* level-schedule depth                                                    */
        LDPC_INFO_SMEM_BYTES = 2,        /* dynamic shared memory per CTA                                            */
        LDPC_INFO_FRAMES_PER_CTA = 3,

@@ -21,6 +21,7 @@
 #include "launch.cuh"
 #include "kernel_gp.cuh"
 #include "kernel_oc.cuh"
+#include "kernel_wf.cuh"
 
 using namespace ldpcb200;
 
@@ -41,6 +42,7 @@ struct Slot {
     // The slot's scratch (d_V, d_MSG, d_LLR0, d_iters) may be used from a caller's stream (decode_device) as well as from the slot's
     // own: `busy` is recorded behind every use and a use from ANOTHER stream waits on it first.
     cudaEvent_t busy = nullptr; cudaStream_t last = nullptr; bool used = false;
+    unsigned int* d_queue = nullptr;                        // warp-per-frame engine (kernel 6): the launch's work-queue counter
 };
 
 }  // namespace
@@ -55,6 +57,10 @@ struct ldpc_b200_handle_s {
     GpMode gp_mode{};
     int32_t* d_cptr = nullptr; int32_t* d_cedge = nullptr;
     OcRow* d_oc_rows = nullptr; int32_t* d_oc_levels = nullptr; int oc_nlevels = 0, oc_F = 0, oc_threads = 0; size_t oc_smem = 0; bool oc_packed_syn = false;   // on-chip generic engine (kernel 5)
+    // warp-per-frame on-chip generic engine (kernel 6)
+    WfRun* d_wf_runs = nullptr; WfVRun* d_wf_vruns = nullptr; uint16_t* d_wf_idx = nullptr; uint16_t* d_wf_cm = nullptr; uint16_t* d_wf_var = nullptr; uint32_t* d_wf_edge_of = nullptr;
+    int wf_nruns = 0, wf_nvruns = 0, wf_melems = 0, wf_cmelems = 0, wf_varelems = 0, wf_npad = 0, wf_warps = 0, wf_ctas_per_sm = 1; size_t wf_smem = 0;
+    uint32_t wf_off_vruns = 0, wf_off_idx = 0, wf_off_cm = 0, wf_off_var = 0, wf_off_state = 0;
     int levels = 0, sms = 0;
     // row-parallel plan
     int rp_G = 0, rp_P = 0, rp_groups = 0, rp_slots = 0, rp_npad = 0, rp_melems = 0, rp_nsteps = 0, rp_nruns = 0, rp_pair_words = 0, rp_static = 0, rp_pair_fastest = 0; size_t rp_smem = 0;
@@ -102,10 +108,10 @@ int validate_params(const ldpc_code_t* c, const ldpc_params_t* p, std::string& w
     if (p->algo < LDPC_ALGO_MS || p->algo > LDPC_ALGO_2NMS) { why = "unknown algo"; return LDPC_ERR_INVALID; }
     if (p->early_term != LDPC_ET_NONE && p->early_term != LDPC_ET_SYNDROME) { why = "unknown early_term"; return LDPC_ERR_INVALID; }
     if (p->out_format != LDPC_OUT_BYTES && p->out_format != LDPC_OUT_PACKED) { why = "unknown out_format"; return LDPC_ERR_INVALID; }
-    if (p->kernel < 0 || p->kernel > 5) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
+    if (p->kernel < 0 || p->kernel > 6) { why = "unknown kernel id"; return LDPC_ERR_INVALID; }
     const bool generic = p->dtype != LDPC_DTYPE_I8 || p->schedule != LDPC_SCHED_LAYERED;
     if (generic && (p->kernel == 1 || p->kernel == 2 || p->kernel == 4)) { why = "kernels 1, 2 and 4 are int8 layered only: int16, float and flooding run on the generic engine (kernel 0 or 3)"; return LDPC_ERR_UNSUPPORTED; }
-    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3 || p->kernel == 5)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
+    for (int i = 0; i < c->nb_deg; i++) if (c->deg[i] > GP_MAXDEG && (generic || p->kernel == 3 || p->kernel == 5 || p->kernel == 6)) { why = "generic engine: row degree > 4096"; return LDPC_ERR_UNSUPPORTED; }
     if (p->dtype == LDPC_DTYPE_F32) {
         if (p->algo == LDPC_ALGO_OMS && (p->offset < 0 || p->llr_scale <= 0)) { why = "float OMS: offset >= 0 and llr_scale > 0 (offset is offset/llr_scale in channel units)"; return LDPC_ERR_INVALID; }
         if ((p->algo == LDPC_ALGO_NMS || p->algo == LDPC_ALGO_2NMS) && !(p->factor1 > 0.0f && p->factor2 > 0.0f)) { why = "float NMS: factors must be positive"; return LDPC_ERR_INVALID; }
@@ -319,10 +325,12 @@ void destroy_impl(ldpc_handle h)
     for (auto& s : h->slot) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         if (s.busy) cudaEventDestroy(s.busy);
+        cudaFree(s.d_queue);
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
     cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2);
     cudaFree(h->d_qy); cudaFree(h->d_qq);
+    cudaFree(h->d_wf_runs); cudaFree(h->d_wf_vruns); cudaFree(h->d_wf_idx); cudaFree(h->d_wf_cm); cudaFree(h->d_wf_var); cudaFree(h->d_wf_edge_of);
     cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge); cudaFree(h->d_oc_rows); cudaFree(h->d_oc_levels);
     free(h->code.pos);
     delete h;
@@ -440,11 +448,104 @@ int launch_decode_oc(ldpc_handle h, const void* d_llr, uint8_t* d_hard, size_t f
     return LDPC_OK;
 }
 
+// ---- warp-per-frame on-chip generic engine (kernel 6): plan = steps of <= 32 same-degree rows (per level when layered), the edge
+// table step-transposed, and for the flooding schedule the column table in steps of 32 consecutive variables --------------------------
+struct WfPlan {
+    std::vector<WfRun> runs; std::vector<uint16_t> idx_t; std::vector<uint32_t> edge_of; std::vector<WfVRun> vruns; std::vector<uint16_t> cm_t, var_t;
+    int m_elems = 0, n_pad = 0, levels = 1; size_t lanes_used = 0, lanes_total = 0;
+};
+
+int build_wf_plan(const ldpc_code_t& c, bool flooding, WfPlan& plan)
+{
+    std::vector<int32_t> level((size_t)c.n_checks, 0);
+    if (!flooding) { plan.levels = ldpc_b200_level_schedule(&c, level.data()); if (plan.levels < 0) return plan.levels; }
+    std::vector<int> row_cls((size_t)c.n_checks); std::vector<uint32_t> row_e0((size_t)c.n_checks);
+    { int r = 0; uint32_t e = 0;
+      for (int k = 0; k < c.nb_deg; k++) for (int q = 0; q < c.rows[k]; q++, r++) { row_cls[r] = k; row_e0[r] = e; e += c.deg[k]; } }
+    std::vector<std::vector<int>> by_level((size_t)plan.levels);
+    for (int r = 0; r < c.n_checks; r++) by_level[level[r]].push_back(r);
+    std::vector<uint32_t> elem_of_edge((size_t)c.m, 0u);
+    uint32_t off = 0;
+    // check-node side: a run = the rows of one (level, degree class) in reference order, cut into steps of 32
+    for (int L = 0; L < plan.levels; L++) {
+        bool first = true;
+        for (int k = 0; k < c.nb_deg; k++) {
+            std::vector<int> rows;
+            for (int r : by_level[L]) if (row_cls[r] == k) rows.push_back(r);
+            if (rows.empty()) continue;
+            const uint32_t d = (uint32_t)c.deg[k], nsteps = (uint32_t)(rows.size() + 31) / 32;
+            WfRun run{}; run.deg = (uint16_t)d; run.cls = (uint16_t)k; run.nsteps = (uint16_t)nsteps; run.last = (uint16_t)(rows.size() - 32 * (nsteps - 1));
+            run.off = off; run.sync = (first && L > 0) ? 1u : 0u;
+            first = false;
+            plan.idx_t.resize(off + 32u * d * nsteps, 0); plan.edge_of.resize(off + 32u * d * nsteps, 0xFFFFFFFFu);
+            for (size_t q = 0; q < rows.size(); q++)
+                for (uint32_t j = 0; j < d; j++) {
+                    const uint32_t ref_e = row_e0[rows[q]] + j, el = off + 32u * ((uint32_t)(q / 32) * d + j) + (uint32_t)(q % 32);
+                    plan.idx_t[el] = (uint16_t)(4 * c.pos[ref_e]); plan.edge_of[el] = ref_e; elem_of_edge[ref_e] = el;
+                }
+            off += 32u * d * nsteps;
+            plan.lanes_used += rows.size(); plan.lanes_total += 32u * nsteps;
+            plan.runs.push_back(run);
+        }
+    }
+    plan.m_elems = (int)off;
+    plan.n_pad = (c.n + 3) / 4 * 4;
+    // variable-node side (flooding): variables sorted by column degree (stable: index order inside a degree), a run = one degree
+    if (flooding) {
+        std::vector<std::vector<uint32_t>> col((size_t)c.n);
+        for (int e = 0; e < c.m; e++) col[c.pos[e]].push_back((uint32_t)e);                 // ascending edge order inside a column
+        size_t maxdv = 0;
+        for (auto& v : col) maxdv = std::max(maxdv, v.size());
+        uint32_t coff = 0, voff = 0;
+        for (size_t dv = 0; dv <= maxdv; dv++) {
+            std::vector<int> vars;
+            for (int v = 0; v < c.n; v++) if (col[v].size() == dv) vars.push_back(v);
+            if (vars.empty()) continue;
+            const uint32_t nsteps = (uint32_t)(vars.size() + 31) / 32;
+            WfVRun run{}; run.dv = (uint16_t)dv; run.nsteps = (uint16_t)nsteps; run.last = (uint16_t)(vars.size() - 32 * (nsteps - 1)); run.off = coff; run.voff = voff;
+            plan.cm_t.resize(coff + 32u * (uint32_t)dv * nsteps, 0); plan.var_t.resize(voff + 32u * nsteps, 0);
+            for (size_t q = 0; q < vars.size(); q++) {
+                plan.var_t[voff + q] = (uint16_t)(4 * vars[q]);
+                for (size_t k = 0; k < dv; k++)
+                    plan.cm_t[coff + 32u * ((uint32_t)(q / 32) * (uint32_t)dv + (uint32_t)k) + (uint32_t)(q % 32)] = (uint16_t)(4 * elem_of_edge[col[vars[q]][k]]);
+            }
+            coff += 32u * (uint32_t)dv * nsteps; voff += 32u * nsteps;
+            plan.vruns.push_back(run);
+        }
+    }
+    return LDPC_OK;
+}
+
+template <class S>
+int launch_decode_wf(ldpc_handle h, Slot& s, const void* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
+{
+    const ldpc_code_t& c = h->code;
+    if (!s.d_queue) CU_TRY(h, cudaMalloc((void**)&s.d_queue, sizeof(unsigned int)));
+    CU_TRY(h, cudaMemsetAsync(s.d_queue, 0, sizeof(unsigned int), st));
+    WfArgs<S> a{};
+    a.llr = reinterpret_cast<const S*>(d_llr); a.hard = d_hard; a.iters_done = d_iters;
+    a.dbg_post = want_debug ? reinterpret_cast<S*>(h->d_dbg_post) : nullptr; a.dbg_msgs = want_debug ? reinterpret_cast<S*>(h->d_dbg_msgs) : nullptr;
+    a.runs = h->d_wf_runs; a.idx_t = h->d_wf_idx; a.vruns = h->d_wf_vruns; a.cm_t = h->d_wf_cm; a.var_t = h->d_wf_var; a.edge_of = h->d_wf_edge_of; a.counter = s.d_queue;
+    a.frames = frames; a.n = c.n; a.m = c.m; a.n_pad = h->wf_npad; a.m_elems = h->wf_melems; a.nruns = h->wf_nruns; a.nvruns = h->wf_nvruns; a.cm_elems = h->wf_cmelems; a.var_elems = h->wf_varelems;
+    a.iters = iters; a.flooding = h->prm.schedule == LDPC_SCHED_FLOODING; a.et = h->prm.early_term == LDPC_ET_SYNDROME; a.packed = h->prm.out_format == LDPC_OUT_PACKED;
+    a.off_vruns = h->wf_off_vruns; a.off_idx = h->wf_off_idx; a.off_cm = h->wf_off_cm; a.off_var = h->wf_off_var; a.off_state = h->wf_off_state; a.md = h->gp_mode;
+    const size_t per_cta = (size_t)h->wf_warps;
+    const int blocks = (int)std::min<size_t>((size_t)h->sms * h->wf_ctas_per_sm, (frames + per_cta - 1) / per_cta);
+    CU_TRY(h, (cudaError_t)launch_wf(a, blocks, h->wf_warps * 32, h->wf_smem, st));
+    h->launches += 1;
+    return LDPC_OK;
+}
+
 // decode `frames` frames that are already in device memory, on stream st.  For the frame-parallel kernel the slot's V/MSG
 // state is used, `frames` must fit it.
 int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, size_t frames, int iters, uint8_t* d_iters, cudaStream_t st, bool want_debug)
 {
     const ldpc_code_t& c = h->code;
+    if (h->kernel == 6) {
+        if (h->elem == 4) return launch_decode_wf<float>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        if (h->elem == 2) return launch_decode_wf<int16_t>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+        return launch_decode_wf<int8_t>(h, s, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
+    }
     if (h->kernel == 5) {
         if (h->elem == 4) return launch_decode_oc<float>(h, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
         if (h->elem == 2) return launch_decode_oc<int16_t>(h, d_llr, d_hard, frames, iters, d_iters, st, want_debug);
@@ -615,7 +716,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
 
     // kernel selection.  int16 / float / flooding -> the generic engine; int8 layered -> the on-chip row-parallel kernel when the
     // whole state of >= 8 frame pairs per SM fits in shared memory, else the frame-parallel kernel
-    const bool generic = params->dtype != LDPC_DTYPE_I8 || params->schedule != LDPC_SCHED_LAYERED || params->kernel == 3 || params->kernel == 5;
+    const bool generic = params->dtype != LDPC_DTYPE_I8 || params->schedule != LDPC_SCHED_LAYERED || params->kernel == 3 || params->kernel == 5 || params->kernel == 6;
     h->elem = params->dtype == LDPC_DTYPE_F32 ? 4 : (params->dtype == LDPC_DTYPE_I16 ? 2 : 1);
     h->kernel = generic ? 3 : 1;
     if (generic) {
@@ -629,8 +730,42 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         CREATE_TRY(cudaMemcpy(h->d_cptr, cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMalloc((void**)&h->d_cedge, cedge.size() * sizeof(int32_t)));
         CREATE_TRY(cudaMemcpy(h->d_cedge, cedge.data(), cedge.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        // on-chip variant (kernel 5): fp32 state of F frames in shared memory, rows in level order (flooding: one level)
         const bool flooding = params->schedule == LDPC_SCHED_FLOODING;
+        // warp-per-frame on-chip variant (kernel 6): one warp owns one frame; chosen when at least 8 frames fit per SM and the schedule
+        // fills the lanes (flooding always does; a layered schedule with narrow levels is better served by kernel 5's (row, frame) tasks)
+        if ((params->kernel == 6 || params->kernel == 0) && code->n <= 16383) {
+            WfPlan plan;
+            if ((rc = build_wf_plan(*code, flooding, plan))) { destroy_impl(h); return fail(nullptr, rc, "level schedule failed"); }
+            auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+            const size_t off_vruns = up16(plan.runs.size() * sizeof(WfRun)), off_idx = up16(off_vruns + plan.vruns.size() * sizeof(WfVRun));
+            const size_t off_cm = up16(off_idx + (size_t)plan.m_elems * 2), off_var = up16(off_cm + plan.cm_t.size() * 2), off_state = up16(off_var + plan.var_t.size() * 2);
+            const size_t frame_bytes = ((size_t)plan.n_pad * (flooding ? 2 : 1) + plan.m_elems) * sizeof(float);
+            const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
+            const int fit = off_state < budget ? (int)((budget - off_state) / frame_bytes) : 0;
+            const bool lanes_ok = plan.lanes_used * 2 >= plan.lanes_total;
+            const bool table_ok = (size_t)plan.m_elems * 4 < 65535;
+            if (params->kernel == 6 && (fit < 1 || !table_ok)) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the warp-per-frame engine"); }
+            if (table_ok && (params->kernel == 6 || (fit >= 8 && lanes_ok))) {
+                // several CTAs per SM when the frames are small: at most WF_MAX_WARPS warps per CTA, all of an SM's shared memory used
+                int ctas = 1, warps = std::min(fit, WF_MAX_WARPS);
+                if (fit > WF_MAX_WARPS) {
+                    const size_t sm_total = (size_t)prop.sharedMemPerMultiprocessor;
+                    ctas = (int)std::min<size_t>(64 / WF_MAX_WARPS, sm_total / (off_state + (size_t)WF_MAX_WARPS * frame_bytes + 1024));
+                    ctas = std::max(ctas, 1);
+                }
+                h->kernel = 6; h->levels = plan.levels; h->wf_warps = warps; h->wf_ctas_per_sm = ctas;
+                h->wf_nruns = (int)plan.runs.size(); h->wf_nvruns = (int)plan.vruns.size(); h->wf_melems = plan.m_elems; h->wf_cmelems = (int)plan.cm_t.size();
+                h->wf_varelems = (int)plan.var_t.size(); h->wf_npad = plan.n_pad;
+                h->wf_off_vruns = (uint32_t)off_vruns; h->wf_off_idx = (uint32_t)off_idx; h->wf_off_cm = (uint32_t)off_cm; h->wf_off_var = (uint32_t)off_var; h->wf_off_state = (uint32_t)off_state;
+                h->wf_smem = off_state + (size_t)warps * frame_bytes;
+                auto up = [&](auto** dptr, const void* src, size_t bytes) { if (cudaMalloc((void**)dptr, std::max<size_t>(bytes, 16)) != cudaSuccess) return false; return bytes == 0 || cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess; };
+                if (!up(&h->d_wf_runs, plan.runs.data(), plan.runs.size() * sizeof(WfRun)) || !up(&h->d_wf_vruns, plan.vruns.data(), plan.vruns.size() * sizeof(WfVRun)) ||
+                    !up(&h->d_wf_idx, plan.idx_t.data(), plan.idx_t.size() * 2) || !up(&h->d_wf_cm, plan.cm_t.data(), plan.cm_t.size() * 2) ||
+                    !up(&h->d_wf_var, plan.var_t.data(), plan.var_t.size() * 2) ||
+                    !up(&h->d_wf_edge_of, plan.edge_of.data(), plan.edge_of.size() * 4)) { destroy_impl(h); return fail(nullptr, LDPC_ERR_CUDA, "uploading the warp-per-frame plan failed"); }
+            }
+        }
+        // on-chip variant (kernel 5): fp32 state of F frames in shared memory, rows in level order (flooding: one level)
         const size_t per_frame = (size_t)(code->n + code->m + (flooding ? code->n : 0)) * sizeof(float);
         // stop criterion on packed hard-decision words (kernel_oc.cuh: oc_pack_bits) where the criterion reads posteriors (float or
         // flooding): n extra words behind the state, frames-per-CTA <= 32
@@ -640,7 +775,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         if (want_syn_words && F > 32) F = (int)std::min<size_t>(OC_MAXF, ((size_t)prop.sharedMemPerBlockOptin - 1024) / per_frame);   // short codes: the per-frame test
         h->oc_packed_syn = want_syn_words && F <= 32;
         if (params->kernel == 5 && F < 1) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "code state does not fit in shared memory for the on-chip generic engine"); }
-        if ((params->kernel == 5 && F >= 1) || (params->kernel == 0 && F >= 8)) {
+        if (h->kernel != 6 && ((params->kernel == 5 && F >= 1) || (params->kernel == 0 && F >= 8))) {
             std::vector<int32_t> level(code->n_checks, 0);
             int levels = 1;
             if (!flooding) { levels = ldpc_b200_level_schedule(code, level.data()); if (levels < 0) { destroy_impl(h); return fail(nullptr, levels, "level schedule failed"); } }
@@ -753,8 +888,8 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     // pipeline granularity of decode(): whole waves of the chosen kernel.  H2D, kernel and D2H take about the same time per
     // frame for 576x288 over PCIe Gen5, so the fill/drain of the 3-stage pipeline costs 2 chunks: many small chunks win
     // (measured with tools/e2e_sweep.py: 5 chunks 1.17 ms, 10 chunks of one wave each 1.11 ms).  reserved[2] overrides (waves per chunk).
-    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : h->kernel == 5 ? (size_t)h->sms * h->oc_F : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
-    size_t k = h->kernel == 2 ? 1 : h->kernel == 5 ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
+    const size_t wave = h->kernel == 2 ? (size_t)h->sms * h->rp_slots * 2 : h->kernel == 6 ? (size_t)h->sms * h->wf_warps * h->wf_ctas_per_sm : h->kernel == 5 ? (size_t)h->sms * h->oc_F : (h->kernel == 3 ? (size_t)h->sms * 1024 : (size_t)h->sms * 512 * 4);
+    size_t k = h->kernel == 2 ? 1 : (h->kernel == 5 || h->kernel == 6) ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
     // frame-parallel kernels: a wave is 300 Ki frames, so the rule above never split a batch and decode() ran H2D, kernel and D2H
@@ -774,8 +909,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     switch (what) {
     case LDPC_INFO_KERNEL: *value = h->kernel; break;
     case LDPC_INFO_LEVELS: *value = h->levels; break;
-    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : h->kernel == 5 ? (int64_t)h->oc_smem : (h->kernel == 1 ? 16384 : 0); break;
-    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : h->kernel == 5 ? h->oc_F : (h->kernel == 4 ? FS_CONSUMERS * 4 : FP_BLOCK * 4)); break;
+    case LDPC_INFO_SMEM_BYTES: *value = h->kernel == 2 ? (int64_t)h->rp_smem : h->kernel == 6 ? (int64_t)h->wf_smem : h->kernel == 5 ? (int64_t)h->oc_smem : (h->kernel == 1 ? 16384 : 0); break;
+    case LDPC_INFO_FRAMES_PER_CTA: *value = h->kernel == 2 ? h->rp_slots * 2 : (h->kernel == 3 ? GP_BLOCK : h->kernel == 6 ? h->wf_warps : h->kernel == 5 ? h->oc_F : (h->kernel == 4 ? FS_CONSUMERS * 4 : FP_BLOCK * 4)); break;
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;

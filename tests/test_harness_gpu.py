@@ -70,7 +70,7 @@ def test_c_simulator_reference_cli(built, code576):
 
 def test_c_simulator_float_flooding_and_code_header(built, tmp_path):
     out, pts = run_sim("-float", "-NMS", 0.75, "-flooding", "-early", "-iter", 40, "-min", 3, "-max", 3, "-fer", 20, "-frames", 8192, "-max-frames", 65536)
-    assert "FLOODING + SYNDROME STOP" in out and "generic engine (fp32 arithmetic, on-chip state)" in out and 3.0 in pts and pts[3.0]["fer"] < 0.01
+    assert "FLOODING + SYNDROME STOP" in out and "generic engine (fp32 arithmetic, on-chip state" in out and 3.0 in pts and pts[3.0]["fer"] < 0.01
     # H-matrix load from a header in the reference's own format
     code = pkg.Code.load("200x100")
     hdr = tmp_path / "constantes_sse.h"
