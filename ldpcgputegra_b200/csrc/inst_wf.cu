@@ -4,26 +4,29 @@
 
 namespace ldpcb200 {
 
-template <class S, bool FLOOD>
+template <class S, bool FLOOD, bool PAIR>
 static int do_wf(const WfArgs<S>& a, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(wf_decode_kernel<S, FLOOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wf_decode_kernel<S, FLOOD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    wf_decode_kernel<S, FLOOD><<<blocks, threads, smem, st>>>(a);
+    wf_decode_kernel<S, FLOOD, PAIR><<<blocks, threads, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
 int launch_wf(const WfArgs<float>& a, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    return a.flooding ? do_wf<float, true>(a, blocks, threads, smem, st) : do_wf<float, false>(a, blocks, threads, smem, st);
+    if (a.pair) return a.flooding ? do_wf<float, true, true>(a, blocks, threads, smem, st) : do_wf<float, false, true>(a, blocks, threads, smem, st);
+    return a.flooding ? do_wf<float, true, false>(a, blocks, threads, smem, st) : do_wf<float, false, false>(a, blocks, threads, smem, st);
 }
 int launch_wf(const WfArgs<int16_t>& a, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    return a.flooding ? do_wf<int16_t, true>(a, blocks, threads, smem, st) : do_wf<int16_t, false>(a, blocks, threads, smem, st);
+    if (a.pair) return a.flooding ? do_wf<int16_t, true, true>(a, blocks, threads, smem, st) : do_wf<int16_t, false, true>(a, blocks, threads, smem, st);
+    return a.flooding ? do_wf<int16_t, true, false>(a, blocks, threads, smem, st) : do_wf<int16_t, false, false>(a, blocks, threads, smem, st);
 }
 int launch_wf(const WfArgs<int8_t>& a, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    return a.flooding ? do_wf<int8_t, true>(a, blocks, threads, smem, st) : do_wf<int8_t, false>(a, blocks, threads, smem, st);
+    if (a.pair) return a.flooding ? do_wf<int8_t, true, true>(a, blocks, threads, smem, st) : do_wf<int8_t, false, true>(a, blocks, threads, smem, st);
+    return a.flooding ? do_wf<int8_t, true, false>(a, blocks, threads, smem, st) : do_wf<int8_t, false, false>(a, blocks, threads, smem, st);
 }
 
 }  // namespace ldpcb200

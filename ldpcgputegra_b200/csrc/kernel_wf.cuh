@@ -58,6 +58,7 @@ struct WfArgs {
     unsigned int* counter;     // work queue: next frame to decode (zeroed before the launch)
     size_t frames;
     int n, m, n_pad, m_elems, nruns, nvruns, cm_elems, var_elems, iters, flooding, et, packed;
+    int pair;                  // two steps of a run per pass (the PAIR instantiation): chosen by the host when an SM holds fewer than 12 frames
     uint32_t off_vruns, off_idx, off_cm, off_var, off_state;      // byte offsets of the shared-memory regions (each 16-byte aligned)
     GpMode md;
 };
@@ -73,62 +74,76 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.
 // sign bit of the result <=> x > 0 (x = +-0 gives +0): the oracle's "x > 0" flag as a bit pattern that can be XOR-ed
 __device__ __forceinline__ uint32_t wf_pos_flag(float x) { return __float_as_uint(__fsub_rn(0.0f, x)); }
 
-// One check row, degree known at compile time.  vb = shared address of the frame's V, msa = shared address of MSG[off + lane],
-// ixa = shared address of idx_t[off + lane].  WRITE_V = layered schedule (posteriors updated in place).
-template <bool FLT, int D, bool WRITE_V>
-__device__ __forceinline__ void wf_row(const GpMode& md, uint32_t vb, uint32_t msa, uint32_t ixa, int cls, bool first)
+// R check rows of R consecutive steps of a run at once (degree known at compile time): all loads first, then the arithmetic of the R
+// independent rows (the compiler interleaves them: instruction-level parallelism is what a warp-per-frame mapping is short of —
+// profiles/r02_ncu_wf_v2.txt: 18 warps per SM, 30 % of the stall samples on fixed-latency dependencies, 20 % on shared-memory loads),
+// then the stores.  vb = shared address of the frame's V, msa = shared address of MSG[off + lane] of the first row, ixa = shared
+// address of idx_t[off + lane]; the next step's row is 32 D elements further.  WRITE_V = layered schedule (posteriors updated in
+// place; rows of one run belong to one level, so they share no variable).
+template <bool FLT, int D, bool WRITE_V, int R>
+__device__ __forceinline__ void wf_rows(const GpMode& md, uint32_t vb, uint32_t msa, uint32_t ixa, int cls, bool first)
 {
-    uint32_t ua[D];
-    float x[D], a[D];
+    uint32_t ua[R][D];
+    float x[R][D], a[R][D], msg[R][D];
 #pragma unroll
-    for (int j = 0; j < D; j++) ua[j] = vb + lds_u16(ixa + 64 * j);
+    for (int r = 0; r < R; r++)
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-        float xx = __fsub_rn(lds_f32(ua[j]), lds_f32(msa + 128 * j));
-        if (!FLT) xx = gp_clamp(xx, md.lo, md.hi);
-        x[j] = xx;
-        a[j] = gp_magnitude<FLT>(md, xx, cls);
-    }
-    float min1 = md.min_init, min2 = md.min_init;
+        for (int j = 0; j < D; j++) ua[r][j] = vb + lds_u16(ixa + 64 * (D * r + j));
 #pragma unroll
-    for (int j = 0; j + 1 < D; j += 2) {      // pairwise merge: the two smallest values (with multiplicity) whatever the order
-        const float p = fminf(a[j], a[j + 1]), q = fmaxf(a[j], a[j + 1]);
-        min2 = fminf(fminf(fmaxf(min1, p), min2), q);
-        min1 = fminf(min1, p);
-    }
-    if (D & 1) { const float old = min1; min1 = fminf(min1, a[D - 1]); min2 = fminf(min2, fmaxf(a[D - 1], old)); }
-    float c1, c2;
-    gp_constants<FLT>(md, min1, min2, cls, first, c1, c2);
-    if (FLT || !md.x86) {
-        // keep the sign iff par ^ (x > 0), par = XOR of all (x > 0) flags — float, ARM_SCALAR and GPU_FIXED (oracle: update_row)
-        uint32_t par = 0x80000000u;                                  // the complement, so that `neg` below comes out directly
-#pragma unroll
-        for (int j = 0; j < D; j++) par ^= wf_pos_flag(x[j]);
+    for (int r = 0; r < R; r++)
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            const float mag = (a[j] == min1) ? c1 : c2;
-            const uint32_t neg = (par ^ wf_pos_flag(x[j])) & 0x80000000u;      // set <=> !(par ^ flag): negate
-            const float msg = __uint_as_float(__float_as_uint(mag) ^ neg);    // ARM_SCALAR's clamp of the signed message is folded into c1/c2 (gp_constants)
-            sts_f32(msa + 128 * j, msg);
-            if (WRITE_V) {
-                float vn = __fadd_rn(x[j], msg);
-                if (!FLT) vn = gp_clamp(vn, md.lo, md.hi);
-                sts_f32(ua[j], vn);
+            float xx = __fsub_rn(lds_f32(ua[r][j]), lds_f32(msa + 128 * (D * r + j)));
+            if (!FLT) xx = gp_clamp(xx, md.lo, md.hi);
+            x[r][j] = xx;
+            a[r][j] = gp_magnitude<FLT>(md, xx, cls);
+        }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float min1 = md.min_init, min2 = md.min_init;
+#pragma unroll
+        for (int j = 0; j + 1 < D; j += 2) {      // pairwise merge: the two smallest values (with multiplicity) whatever the order
+            const float p = fminf(a[r][j], a[r][j + 1]), q = fmaxf(a[r][j], a[r][j + 1]);
+            min2 = fminf(fminf(fmaxf(min1, p), min2), q);
+            min1 = fminf(min1, p);
+        }
+        if (D & 1) { const float old = min1; min1 = fminf(min1, a[r][D - 1]); min2 = fminf(min2, fmaxf(a[r][D - 1], old)); }
+        float c1, c2;
+        gp_constants<FLT>(md, min1, min2, cls, first, c1, c2);
+        if (FLT || !md.x86) {
+            // keep the sign iff par ^ (x > 0), par = XOR of all (x > 0) flags — float, ARM_SCALAR and GPU_FIXED (oracle: update_row)
+            uint32_t par = 0x80000000u;                                  // the complement, so that `neg` below comes out directly
+#pragma unroll
+            for (int j = 0; j < D; j++) par ^= wf_pos_flag(x[r][j]);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const float mag = (a[r][j] == min1) ? c1 : c2;
+                const uint32_t neg = (par ^ wf_pos_flag(x[r][j])) & 0x80000000u;      // set <=> !(par ^ flag): negate
+                msg[r][j] = __uint_as_float(__float_as_uint(mag) ^ neg);             // ARM_SCALAR's clamp of the signed message is folded into c1/c2 (gp_constants)
+            }
+        } else {
+            // x86 semantics: sign bit, zero counts positive, degree-parity term (ref: CDecoder_OMS_fixed_SSE.cpp:180-190,232-244)
+            int par = D & 1;
+#pragma unroll
+            for (int j = 0; j < D; j++) par ^= (x[r][j] < 0.0f);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const float mag = (a[r][j] == min1) ? c1 : c2;
+                msg[r][j] = (par ^ (int)(x[r][j] < 0.0f)) ? -mag : mag;
             }
         }
-    } else {
-        // x86 semantics: sign bit, zero counts positive, degree-parity term (ref: CDecoder_OMS_fixed_SSE.cpp:180-190,232-244)
-        int par = D & 1;
+    }
 #pragma unroll
-        for (int j = 0; j < D; j++) par ^= (x[j] < 0.0f);
+    for (int r = 0; r < R; r++)
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            const float mag = (a[j] == min1) ? c1 : c2;
-            const float msg = (par ^ (int)(x[j] < 0.0f)) ? -mag : mag;
-            sts_f32(msa + 128 * j, msg);
-            if (WRITE_V) sts_f32(ua[j], gp_clamp(__fadd_rn(x[j], msg), md.lo, md.hi));
+            sts_f32(msa + 128 * (D * r + j), msg[r][j]);
+            if (WRITE_V) {
+                float vn = __fadd_rn(x[r][j], msg[r][j]);
+                if (!FLT) vn = gp_clamp(vn, md.lo, md.hi);
+                sts_f32(ua[r][j], vn);
+            }
         }
-    }
 }
 
 // run-time degree (rows wider than 8): two passes, contributions recomputed from shared memory in the second
@@ -182,40 +197,62 @@ __device__ __forceinline__ uint32_t wf_row_syndrome(const GpMode& md, uint32_t v
     return par & 0x80000000u;
 }
 
-// stop criterion of one row, degree known at compile time (see wf_row_syndrome)
-template <bool POSTERIOR, int D>
-__device__ __forceinline__ uint32_t wf_row_syndrome_d(const GpMode& md, uint32_t vb, uint32_t msa, uint32_t ixa)
+// stop criterion of R rows of consecutive steps, degree known at compile time (see wf_row_syndrome)
+template <bool POSTERIOR, int D, int R>
+__device__ __forceinline__ uint32_t wf_rows_syndrome(const GpMode& md, uint32_t vb, uint32_t msa, uint32_t ixa)
 {
-    uint32_t f[D];
+    uint32_t ua[R][D];
+    float xx[R][D];
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-        float xx = lds_f32(vb + lds_u16(ixa + 64 * j));
-        if (!POSTERIOR) xx = gp_clamp(xx - lds_f32(msa + 128 * j), md.lo, md.hi);
-        f[j] = wf_pos_flag(xx);
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int j = 0; j < D; j++) ua[r][j] = vb + lds_u16(ixa + 64 * (D * r + j));
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            xx[r][j] = lds_f32(ua[r][j]);
+            if (!POSTERIOR) xx[r][j] = gp_clamp(xx[r][j] - lds_f32(msa + 128 * (D * r + j)), md.lo, md.hi);
+        }
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint32_t par = 0u;
+#pragma unroll
+        for (int j = 0; j + 1 < D; j += 2) par = xor3(par, wf_pos_flag(xx[r][j]), wf_pos_flag(xx[r][j + 1]));
+        if (D & 1) par ^= wf_pos_flag(xx[r][D - 1]);
+        bad |= par;
     }
-    uint32_t par = 0u;
-#pragma unroll
-    for (int j = 0; j + 1 < D; j += 2) par = xor3(par, f[j], f[j + 1]);
-    if (D & 1) par ^= f[D - 1];
-    return par & 0x80000000u;
+    return bad & 0x80000000u;
 }
 
-// variable-node update of one variable of column degree DV (flooding): clamp(llr + sum of the column's messages), ascending edge order
-template <bool FLT, int DV>
-__device__ __forceinline__ void wf_var(const GpMode& md, uint32_t vb, uint32_t lb, uint32_t mb, uint32_t ca, uint32_t ta)
+// variable-node update of R variables (of R consecutive steps) of column degree DV (flooding): clamp(llr + sum of the column's
+// messages), ascending edge order.  ca = shared address of cm_t[off + lane], ta = shared address of var_t[voff + lane].
+template <bool FLT, int DV, int R>
+__device__ __forceinline__ void wf_vars(const GpMode& md, uint32_t vb, uint32_t lb, uint32_t mb, uint32_t ca, uint32_t ta)
 {
-    const uint32_t va = lds_u16(ta);
-    uint32_t off[DV];
+    uint32_t va[R], off[R][DV > 0 ? DV : 1];
+    float s[R], mk[R][DV > 0 ? DV : 1];
 #pragma unroll
-    for (int k = 0; k < DV; k++) off[k] = lds_u16(ca + 64 * k);
-    float s = lds_f32(lb + va);
-    float mk[DV];
+    for (int r = 0; r < R; r++) {
+        va[r] = lds_u16(ta + 64 * r);
 #pragma unroll
-    for (int k = 0; k < DV; k++) mk[k] = lds_f32(mb + off[k]);
+        for (int k = 0; k < DV; k++) off[r][k] = lds_u16(ca + 64 * (DV * r + k));
+    }
 #pragma unroll
-    for (int k = 0; k < DV; k++) s = __fadd_rn(s, mk[k]);
-    if (!FLT) s = gp_clamp(s, md.lo, md.hi);
-    sts_f32(vb + va, s);
+    for (int r = 0; r < R; r++) {
+        s[r] = lds_f32(lb + va[r]);
+#pragma unroll
+        for (int k = 0; k < DV; k++) mk[r][k] = lds_f32(mb + off[r][k]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int k = 0; k < DV; k++) s[r] = __fadd_rn(s[r], mk[r][k]);
+        if (!FLT) s[r] = gp_clamp(s[r], md.lo, md.hi);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) sts_f32(vb + va[r], s[r]);
 }
 template <bool FLT>
 __device__ __noinline__ void wf_var_rt(const GpMode& md, uint32_t vb, uint32_t lb, uint32_t mb, uint32_t ca, uint32_t ta, int dv)
@@ -228,7 +265,10 @@ __device__ __noinline__ void wf_var_rt(const GpMode& md, uint32_t vb, uint32_t l
     sts_f32(vb + va, s);
 }
 
-template <class S, bool FLOOD>
+// PAIR = two steps of a run per pass through the row code (for codes whose state leaves an SM only a few warps: the second row is the
+// latency hiding the missing warps would have been — 2304x1152 float flooding, 4 warps per SM: 4.8 -> 6.4 M frames/s; with 18 warps
+// per SM the doubled code only costs instruction-cache misses: 576x288 48 -> 41 M frames/s, profiles/r02_sweep_wf_v3.jsonl)
+template <class S, bool FLOOD, bool PAIR>
 __global__ void __launch_bounds__(WF_MAX_WARPS * 32, 1) wf_decode_kernel(const __grid_constant__ WfArgs<S> A)
 {
     constexpr bool FLT = GpIsFloat<S>::value;
@@ -287,10 +327,12 @@ __global__ void __launch_bounds__(WF_MAX_WARPS * 32, 1) wf_decode_kernel(const _
                 if (!FLOOD && rd.w) __syncwarp();                  // a new level reads what the previous one wrote
                 uint32_t msa = mb + 4u * (rd.z + (uint32_t)lane), ixa = idx_s + 2u * (rd.z + (uint32_t)lane);
 #define WF_CASE(DD)                                                                                                             \
-    case DD:                                                                                                                    \
-        for (int s = 0; s < nsteps; s++, msa += 128u * DD, ixa += 64u * DD)                                                     \
-            if (s + 1 < nsteps || lane < last) wf_row<FLT, DD, !FLOOD>(md, vb, msa, ixa, cls, first);                          \
-        break;
+    case DD: {                                                                                                                  \
+        int s = 0;                                                                                                              \
+        for (; PAIR && s + 2 < nsteps; s += 2, msa += 256u * DD, ixa += 128u * DD) wf_rows<FLT, DD, !FLOOD, PAIR ? 2 : 1>(md, vb, msa, ixa, cls, first); /* full steps, two at a time */ \
+        for (; s < nsteps; s++, msa += 128u * DD, ixa += 64u * DD)                                                              \
+            if (s + 1 < nsteps || lane < last) wf_rows<FLT, DD, !FLOOD, 1>(md, vb, msa, ixa, cls, first);                      \
+    } break;
                 switch (deg) {
                     WF_CASE(3) WF_CASE(4) WF_CASE(5) WF_CASE(6) WF_CASE(7) WF_CASE(8)
                 default:
@@ -308,10 +350,12 @@ __global__ void __launch_bounds__(WF_MAX_WARPS * 32, 1) wf_decode_kernel(const _
                     const int dv = (int)(rd.x & 0xFFFFu), nsteps = (int)(rd.y & 0xFFFFu), last = (int)(rd.y >> 16);
                     uint32_t ca = cm_s + 2u * (rd.z + (uint32_t)lane), ta = vt_s + 2u * (rd.w + (uint32_t)lane);
 #define WF_VCASE(DD)                                                                                                            \
-    case DD:                                                                                                                    \
-        for (int s = 0; s < nsteps; s++, ca += 64u * DD, ta += 64u)                                                             \
-            if (s + 1 < nsteps || lane < last) wf_var<FLT, DD>(md, vb, lb, mb, ca, ta);                                        \
-        break;
+    case DD: {                                                                                                                  \
+        int s = 0;                                                                                                              \
+        for (; PAIR && s + 2 < nsteps; s += 2, ca += 128u * DD, ta += 128u) wf_vars<FLT, DD, PAIR ? 2 : 1>(md, vb, lb, mb, ca, ta);                \
+        for (; s < nsteps; s++, ca += 64u * DD, ta += 64u)                                                                      \
+            if (s + 1 < nsteps || lane < last) wf_vars<FLT, DD, 1>(md, vb, lb, mb, ca, ta);                                    \
+    } break;
                     switch (dv) {
                         WF_VCASE(1) WF_VCASE(2) WF_VCASE(3) WF_VCASE(4) WF_VCASE(5) WF_VCASE(6)
                     default:
@@ -323,30 +367,36 @@ __global__ void __launch_bounds__(WF_MAX_WARPS * 32, 1) wf_decode_kernel(const _
                 __syncwarp();
             }
             it++;
-            // ---- per-frame stop criterion ----
+            // ---- per-frame stop criterion: leaves at the first step that holds an unsatisfied check (early iterations fail at once) ----
             if (A.et && it < A.iters) {
-                uint32_t bad = 0u;
+                bool bad_any = false;
 #pragma unroll 1
-                for (int r = 0; r < A.nruns; r++) {
+                for (int r = 0; r < A.nruns && !bad_any; r++) {
                     const uint4 rd = lds_u128(runs_s + 16u * r);
                     const int deg = (int)(rd.x & 0xFFFFu), nsteps = (int)(rd.y & 0xFFFFu), last = (int)(rd.y >> 16);
                     uint32_t msa = mb + 4u * (rd.z + (uint32_t)lane), ixa = idx_s + 2u * (rd.z + (uint32_t)lane);
 #define WF_SCASE(DD)                                                                                                            \
     case DD:                                                                                                                    \
-        for (int s = 0; s < nsteps; s++, msa += 128u * DD, ixa += 64u * DD)                                                     \
+        for (int s = 0; s < nsteps && !bad_any; s++, msa += 128u * DD, ixa += 64u * DD) {                                       \
+            uint32_t bad = 0u;                                                                                                  \
             if (s + 1 < nsteps || lane < last)                                                                                  \
-                bad |= posterior_syndrome ? wf_row_syndrome_d<true, DD>(md, vb, msa, ixa) : wf_row_syndrome_d<false, DD>(md, vb, msa, ixa); \
+                bad = posterior_syndrome ? wf_rows_syndrome<true, DD, 1>(md, vb, msa, ixa) : wf_rows_syndrome<false, DD, 1>(md, vb, msa, ixa); \
+            bad_any = __any_sync(0xFFFFFFFFu, bad);                                                                             \
+        }                                                                                                                       \
         break;
                     switch (deg) {
                         WF_SCASE(3) WF_SCASE(4) WF_SCASE(5) WF_SCASE(6) WF_SCASE(7) WF_SCASE(8)
                     default:
-                        for (int s = 0; s < nsteps; s++, msa += 128u * deg, ixa += 64u * deg)
+                        for (int s = 0; s < nsteps && !bad_any; s++, msa += 128u * deg, ixa += 64u * deg) {
+                            uint32_t bad = 0u;
                             if (s + 1 < nsteps || lane < last)
-                                bad |= posterior_syndrome ? wf_row_syndrome<true>(md, vb, msa, ixa, deg) : wf_row_syndrome<false>(md, vb, msa, ixa, deg);
+                                bad = posterior_syndrome ? wf_row_syndrome<true>(md, vb, msa, ixa, deg) : wf_row_syndrome<false>(md, vb, msa, ixa, deg);
+                            bad_any = __any_sync(0xFFFFFFFFu, bad);
+                        }
                     }
 #undef WF_SCASE
                 }
-                if (!__any_sync(0xFFFFFFFFu, bad)) break;
+                if (!bad_any) break;
             }
         }
         // ---- outputs ----

@@ -529,6 +529,7 @@ int launch_decode_wf(ldpc_handle h, Slot& s, const void* d_llr, uint8_t* d_hard,
     a.frames = frames; a.n = c.n; a.m = c.m; a.n_pad = h->wf_npad; a.m_elems = h->wf_melems; a.nruns = h->wf_nruns; a.nvruns = h->wf_nvruns; a.cm_elems = h->wf_cmelems; a.var_elems = h->wf_varelems;
     a.iters = iters; a.flooding = h->prm.schedule == LDPC_SCHED_FLOODING; a.et = h->prm.early_term == LDPC_ET_SYNDROME; a.packed = h->prm.out_format == LDPC_OUT_PACKED;
     a.off_vruns = h->wf_off_vruns; a.off_idx = h->wf_off_idx; a.off_cm = h->wf_off_cm; a.off_var = h->wf_off_var; a.off_state = h->wf_off_state; a.md = h->gp_mode;
+    a.pair = h->wf_warps * h->wf_ctas_per_sm < 12;
     const size_t per_cta = (size_t)h->wf_warps;
     const int blocks = (int)std::min<size_t>((size_t)h->sms * h->wf_ctas_per_sm, (frames + per_cta - 1) / per_cta);
     CU_TRY(h, (cudaError_t)launch_wf(a, blocks, h->wf_warps * 32, h->wf_smem, st));
