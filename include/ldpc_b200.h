@@ -117,7 +117,8 @@ typedef struct {
     int32_t reserved[5];  /* 0 for production use.  Experiment knobs of this implementation, used by tools/ and the A/B tests only:
                              [0],[1] = (warps, pairs) of an on-chip group; [2] = kernel waves per pipeline chunk of decode();
                              [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping;
-                             [4] = stage-ring depth of the staged kernel (bits 0..7) | its CTA width (bits 8..: 1 = 128, 2 = 256 consumer threads) */
+                             [4] = stage-ring depth of the staged kernel (bits 0..7) | its CTA width (bits 8..11: 1 = 128, 2 = 256 consumer threads)
+                                   | message lines through a TMA tensor map (bits 12..13: 1 = never, 2 = always) */
 } ldpc_params_t;
 
 typedef struct ldpc_b200_handle_s* ldpc_handle;

@@ -214,7 +214,13 @@ def default_params(**kw) -> ParamsT:
             p.reserved[4] = (p.reserved[4] & ~255) | int(v)
             continue
         if k == "fs_nc":          # consumer threads per CTA of the staged kernel: 128 | 256 (A/B experiments)
-            p.reserved[4] = (p.reserved[4] & 255) | ({128: 1, 256: 2}[int(v)] << 8)
+            p.reserved[4] = (p.reserved[4] & ~(15 << 8)) | ({128: 1, 256: 2}[int(v)] << 8)
+            continue
+        if k == "fs_tma":         # staged kernel: message lines of a row as one 2-D tensor-map copy: 0 = library's choice, 1 = never, 2 = always (A/B experiments)
+            p.reserved[4] = (p.reserved[4] & ~(3 << 12)) | (int(v) << 12)
+            continue
+        if k == "fs_g4":          # staged kernel: posterior lines through tile::gather4: 0 = library's choice, 1 = never, 2 = always (A/B experiments)
+            p.reserved[4] = (p.reserved[4] & ~(3 << 14)) | (int(v) << 14)
             continue
         if k == "no_pair_fastest":   # keep lane -> (pair t / nrows, row t % nrows) in the static plan (A/B experiments)
             p.reserved[3] = 5 if v else 0

@@ -24,6 +24,7 @@
 // per-frame stop criterion (fs_syndrome_sweep) and a CTA-wide exit.
 // Roofline: HBM, 4*M bytes per frame-iteration as for kernel_fp.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only: the encoder is looked up at run time, ldpc_b200.cu)
 #include "kernel_fp.cuh"
 
 namespace ldpcb200 {
@@ -57,7 +58,12 @@ struct FsArgs {
     uint8_t* iters_done;     // [4*T], nullable
     int et;                  // per-frame syndrome early termination (the ET instantiation)
     int nc;                  // consumer threads per CTA (128 | 256): a staged line is nc * 4 bytes
+    int use_tm;              // the message lines of a row arrive as ONE 2-D tensor copy (box = nc words x row degree over MSG[m][T])
+    int use_g4;              // the posterior lines arrive four at a time (tile::gather4 over V[n][T]); hazard lines come along and are ignored
+    int msg_line0;           // first message line of a stage: max_deg, or max_deg rounded up to 4 with gather4 (it writes whole groups of four)
     ldpc_params_t prm;
+    alignas(64) CUtensorMap tm_msg[LDPC_MAX_DEG_CLASSES];    // one map per degree class: the box height is part of the map
+    alignas(64) CUtensorMap tm_v;                            // gather4: box = nc words x 1 row
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -72,6 +78,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// tensor-map form: box {NC words, D rows} of MSG[m][T] at (t0, e) -> D consecutive lines of the stage (SASS UTMALDG)
+__device__ __forceinline__ void tma_g2s_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// four rows of V[n][T] given by index, nc words each at column t0 -> four consecutive lines of the stage (sm_100 tile::gather4)
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, int c0, int r0, int r1, int r2, int r3, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 // generic-proxy global writes -> visible to later async-proxy (bulk copy) reads.  The .global form is a bare FENCE.VIEW.ASYNC.G;
 // the unqualified form costs a MEMBAR.ALL.GPU on top (cuobjdump)
@@ -122,7 +140,7 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, u
         }
     }
 #pragma unroll
-    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.max_deg + j) * LINE + 4 * tid);
+    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.msg_line0 + j) * LINE + 4 * tid);
     fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);        // ET: frozen frames keep their state
     fence_proxy_async_global();                    // the previous rows' stores, before any later bulk copy of the same lines
     __syncwarp();
@@ -184,7 +202,7 @@ __device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int 
             const uint32_t st = ring + (uint32_t)c.stage * stage_bytes + 4u * (uint32_t)tid;
             uint32_t p0 = dpar, p1 = dpar;
             for (int j = 0; j < D; j++) {
-                const uint32_t wv = lds_u32(st + j * LINE), wm = lds_u32(st + (A.max_deg + j) * LINE);
+                const uint32_t wv = lds_u32(st + j * LINE), wm = lds_u32(st + (A.msg_line0 + j) * LINE);
                 const h2 x0 = __hmin2(__hfma2_sat(bytes01_to_w(wv, K.c64), inv256, __hfma2(bytes01_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
                 const h2 x1 = __hmin2(__hfma2_sat(bytes23_to_w(wv, K.c64), inv256, __hfma2(bytes23_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
                 p0 ^= h2_bits(__hadd2(x0, lo_np));
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     const uint32_t bars = smem_u32(fs_smem);
     const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
     const uint32_t ring = fwd_s + FS_FWD * (uint32_t)A.max_deg * LINE;
-    const uint32_t stage_bytes = (uint32_t)(2 * A.max_deg) * LINE;
+    const uint32_t stage_bytes = (uint32_t)(A.msg_line0 + A.max_deg) * LINE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * NC;
     if (threadIdx.x == 0) {
@@ -223,30 +241,53 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
 
     if (warp >= NC / 32) {
         // ---------------- two producer warps: warp NC/32 fetches the posterior lines of every row, warp NC/32 + 1 its message lines.
-        // Both arrive on the stage's "full" barrier (count 2) with their own byte counts.
+        // Both arrive on the stage's "full" barrier (count 2) with their own byte counts.  (Four producer warps, the edges of a row dealt
+        // out alternately to the two warps of a side, changed nothing — profiles/r02_sweep_fs_pw4.jsonl: the copies are serialised further
+        // down, not in the issuing warp.)
         const bool msg_side = warp > NC / 32;
         int stage = 0; uint32_t phase = 0;
         const int j = lane & 15;
+        const bool mine = lane < 16;
         // ET: every iteration but the last is followed by a second pass over the rows for the stop criterion (sweep 1: every line of
         // every row, hazard flags ignored), each pass behind a CTA barrier so that nothing it reads can be stale
+        // The row's edge words are fetched ONE ROW AHEAD (pos2 is padded by FS_MAXDEG words; the words fetched across a class or pass
+        // boundary belong to the row that follows in memory order, which is the next row except at the wrap-around, where they are
+        // re-read): the load used to sit at the head of every row's dependency chain, and at small batches the producers' time per
+        // row IS the kernel's (profiles/r02_ncu_fs_small.txt: the consumers poll the full barrier 67 times per row).
+        const bool idx_lane = !msg_side && mine;
         for (int it = 0; it < A.iters; it++) {
             const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
             for (int sw = 0; sw < sweeps; sw++) {
                 size_t e = 0;
+                uint32_t p2n = (idx_lane && j < A.deg[0]) ? __ldg(A.pos2 + j) : FS_F_HAZARD;
                 for (int c = 0; c < A.nb_deg; c++) {
                     const int D = A.deg[c];
                     for (int r = 0; r < A.rows[c]; r++, e += D) {
-                        uint32_t p2 = (!msg_side && lane < 16 && j < D) ? __ldg(A.pos2 + e + j) : FS_F_HAZARD;     // issued before the wait: the latencies overlap
-                        if (sw == 1 && !msg_side && lane < 16 && j < D) p2 &= ~FS_F_HAZARD;
+                        uint32_t p2 = (idx_lane && j < D) ? p2n : FS_F_HAZARD;
+                        {   // next row in memory order: same class, or the first row of the next class
+                            const int Dn = (r + 1 < A.rows[c] || c + 1 >= A.nb_deg) ? D : A.deg[c + 1];
+                            p2n = (idx_lane && j < Dn) ? __ldg(A.pos2 + e + D + j) : FS_F_HAZARD;
+                        }
+                        if (sw == 1 && idx_lane && j < D) p2 &= ~FS_F_HAZARD;
                         if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
                         __syncwarp();
-                        const bool go = msg_side ? (lane < 16 && j < D && (it > 0 || sw == 1)) : !(p2 & FS_F_HAZARD);
+                        const bool want_msg = it > 0 || sw == 1;
+                        const int groups = (D + 3) >> 2;                       // gather4: lane g < groups fetches edges 4g .. 4g+3 (the last one repeated to fill the group)
+                        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                        if (!msg_side && A.use_g4) {
+                            const int b = 4 * min(lane, groups - 1);
+                            r0 = (int)(__shfl_sync(0xFFFFFFFFu, p2, b) & FS_IDX_MASK); r1 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 1, D - 1)) & FS_IDX_MASK);
+                            r2 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 2, D - 1)) & FS_IDX_MASK); r3 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 3, D - 1)) & FS_IDX_MASK);
+                        }
+                        const bool go = msg_side ? (mine && want_msg && (A.use_tm ? lane == 0 : j < D)) : (A.use_g4 ? lane < groups : !(p2 & FS_F_HAZARD));
                         const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
                         const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
-                        if (lane == 0) mbar_arrive_expect_tx(full, n_lines * LINE);
+                        if (lane == 0) mbar_arrive_expect_tx(full, ((msg_side && A.use_tm) ? (want_msg ? (uint32_t)D : 0u) : (!msg_side && A.use_g4) ? 4u * n_lines : n_lines) * LINE);
                         __syncwarp();
                         if (go) {
-                            if (msg_side) bulk_g2s(dst0 + (A.max_deg + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                            if (msg_side && A.use_tm) tma_g2s_2d(dst0 + A.msg_line0 * LINE, &A.tm_msg[c], t0, (int)e, full);
+                            else if (msg_side) bulk_g2s(dst0 + (A.msg_line0 + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                            else if (A.use_g4) tma_gather4(dst0 + 4u * (uint32_t)lane * LINE, &A.tm_v, t0, r0, r1, r2, r3, full);
                             else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
                         }
                         if (++stage == Kst) { stage = 0; phase ^= 1u; }

@@ -7,6 +7,7 @@
 // cuts the batch into chunks and runs H2D / decode / D2H of consecutive chunks on rotating stream slots so the three
 // overlap (the pipeline ldpc_multiStream intended: code/ldpc_multiStream/queue/handler.cpp:51-138).
 // There is NO CPU fallback: without a CUDA device every compute entry point returns LDPC_ERR_NO_DEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -87,6 +88,29 @@ int fail(ldpc_handle h, int status, const std::string& msg)
 #define CU_TRY(h, call)                                                                                         \
     do { cudaError_t e__ = (call);                                                                              \
          if (e__ != cudaSuccess) return fail(h, LDPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: no link-time dependency on libcuda
+typedef CUresult (*tm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tm_encode_fn tm_encoder()
+{
+    static tm_encode_fn fn = [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return (tm_encode_fn)p;
+    }();
+    return fn;
+}
+// 2-D map over a state array X[rows][T] of 32-bit words, box = nc words x box_rows rows
+bool make_state_map(CUtensorMap* tm, uint32_t* base, size_t rows, int T, int nc, int box_rows)
+{
+    tm_encode_fn enc = tm_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)T, (cuuint64_t)rows }, strides[1] = { (cuuint64_t)T * 4 };
+    const cuuint32_t box[2] = { (cuuint32_t)nc, (cuuint32_t)box_rows }, estr[2] = { 1, 1 };
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int lo_rail(const ldpc_params_t& p) { return p.semantics == LDPC_SEM_GPU_FIXED ? -128 : -p.sat_var; }
 int hi_rail(const ldpc_params_t& p) { return p.semantics == LDPC_SEM_ARM_SCALAR ? p.sat_var : 127; }
@@ -584,7 +608,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     // the producers).  A/B on one box, DVB-S2: 256 Ki frames 464 vs 493 ms, 128 Ki 276 vs 260 ms, 64 Ki 274 vs 209 ms — the wide
     // CTA wins once there are two of them for every SM.  reserved[4] bits 8.. force 128 (1) or 256 (2).
     const size_t fs_words = (t4 + 255) / 256 * 256;
-    const int fs_knob = h->prm.reserved[4] >> 8;
+    const int fs_knob = (h->prm.reserved[4] >> 8) & 15;
     const int fs_nc = h->fs_max_deg > 8 ? FS_CONSUMERS : fs_knob == 2 ? 256 : fs_knob == 1 ? FS_CONSUMERS
                     : (fs_words / 256 >= (size_t)(2 * h->sms * 17 / 20) ? 256 : FS_CONSUMERS);
     const int tq = h->kernel != 4 ? 32 : fs_nc;
@@ -620,7 +644,27 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
         const int ctas = T / nc, per_sm = std::min(nc == 128 ? 4 : 2, std::max(1, (ctas + h->sms - 1) / h->sms));
-        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)2 * f.max_deg * line, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
+        // message lines as one 2-D tensor copy per row (TMA tensor map) instead of D one-dimensional bulk copies, posterior lines four
+        // at a time (tile::gather4): the copy engine serves requests one after the other (~46 cycles each), which is what bounds a
+        // batch too small to put 16 consumer warps on an SM.  reserved[4] bits 12..13 (message map) and 14..15 (gather4): 1 = never,
+        // 2 = always; default: both whenever the encoder is available.  A/B on one box (profiles/r02_sweep_fs_g4.jsonl), DVB-S2, bulk ->
+        // message map -> + gather4: 16 Ki frames 243 -> 225 -> 195 ms, 64 Ki 246 -> 230 -> 201 ms, 128 Ki 306 -> 291 -> 266 ms, 303 104
+        // frames 521 -> 514 -> 514 ms (gather4 fetches the hazard lines too; the balanced batch does not notice).
+        const int tm_knob = (h->prm.reserved[4] >> 12) & 3, g4_knob = (h->prm.reserved[4] >> 14) & 3;
+        f.use_tm = f.use_g4 = 0;
+        if (tm_knob != 1 && iters > 0) {
+            bool ok = true;
+            for (int i = 0; i < c.nb_deg && ok; i++) ok = make_state_map(&f.tm_msg[i], s.d_MSG, (size_t)c.m, T, nc, c.deg[i]);
+            if (!ok && tm_knob == 2) return fail(h, LDPC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available or refused the message map");
+            f.use_tm = ok ? 1 : 0;
+        }
+        if (iters > 0 && g4_knob != 1) {
+            const bool ok = make_state_map(&f.tm_v, s.d_V, (size_t)c.n, T, nc, 1);
+            if (!ok && g4_knob == 2) return fail(h, LDPC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available or refused the posterior map");
+            f.use_g4 = ok ? 1 : 0;
+        }
+        f.msg_line0 = f.use_g4 ? (f.max_deg + 3) / 4 * 4 : f.max_deg;
+        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.max_deg) * line, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob
