@@ -407,7 +407,7 @@ def run_float_flooding(torch, pkg, ranks, rank, local_rank, F, steps, warmup):
                                 "against 148 SM x 128 lanes x clock"},
            "hbm_roofline": {"bound": "hbm", "achieved": (fps / world) * bytes_per_frame / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": (fps / world) * bytes_per_frame / 1e9 / hbm_peak,
                             "algorithmic_bytes_per_frame": bytes_per_frame, "peak_source": peak_src},
-           "gpu_launches": launches, "kernel": {3: "generic engine (HBM state)", 5: "generic engine, on-chip state", 6: "float flooding, on-chip state"}.get(kernel, str(kernel)),
+           "gpu_launches": launches, "kernel": {3: "generic engine (HBM state)", 5: "generic engine, on-chip state, a CTA owns F frames", 6: "generic engine, on-chip state, one warp per frame (work queue)"}.get(kernel, str(kernel)),
            "clocks": clocks, "ber_fer": {"frames": F, "bit_errors": be, "frame_errors": fe, "fer": fe / F}}
     # e2e: float LLRs in from pinned host memory (4 bytes per bit), hard-decision bytes out
     h_llr, h_hard = pkg.PinnedArray((F, n), np.float32), pkg.PinnedArray((F, n), np.uint8)

@@ -79,6 +79,25 @@ public:
 #ifdef LDPC_B200_DERIVE_GPU
         : CGPUDecoder(0, n, k, m)
 #endif
+    { init(_nb_frames, n, k, m, code, algo, device); }
+
+#if defined(_N) && defined(_K) && defined(_M) && defined(NB_DEGRES) && defined(DEG_1)
+    // The reference's own constructor shape (ref: CGPU_Decoder_OMS_SIMD(nb_frames, n, k, m), code/gpu_fixed/decoder_oms/CGPU_Decoder_OMS_SIMD.h:7):
+    // inside the reference tree the code table is the compiled-in PosNoeudsVariable[_M] (matrix/<code>/constantes_decoder.h, declared by
+    // matrix/<code>/constantes_gpu.h:39), so the only line a harness changes is the `new` expression itself.
+    CGPU_Decoder_B200(size_t _nb_frames, size_t n, size_t k, size_t m, const char* algo = "OMS", int device = 0)
+#ifdef LDPC_B200_DERIVE_GPU
+        : CGPUDecoder(0, n, k, m)
+#endif
+    {
+        static uint32_t table[_M];
+        const ldpc_code_t code = ldpc_b200_adapters::code_from_reference_macros(PosNoeudsVariable, table);
+        init(_nb_frames, n, k, m, code, algo, device);
+    }
+#endif
+
+private:
+    void init(size_t _nb_frames, size_t n, size_t k, size_t m, const ldpc_code_t& code, const char* algo, int device)
     {
         if ((size_t)code.n != n || (size_t)code.n_checks != k || (size_t)code.m != m) { printf("(EE) code table does not match (n,k,m)\n"); exit(0); }
         frames_ = 4 * _nb_frames;
@@ -89,6 +108,8 @@ public:
         int rc = ldpc_b200_create(&h_, &code, &p, device, frames_);
         if (rc) ldpc_b200_adapters::die(nullptr, rc, "create");
     }
+
+public:
     virtual ~CGPU_Decoder_B200() { ldpc_b200_destroy(h_); }
     virtual void initialize() {}
     virtual void decode(float var_nodes[], int Rprime_fix[], int nombre_iterations)

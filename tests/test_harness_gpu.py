@@ -121,3 +121,29 @@ def test_encoder_null_stream_is_safe_without_synchronisation(built, code576):
         assert (be, fe) == (0, 0), f"batch {b}: {be} bit errors at sigma 0.05"
         assert int(d_cw.sum().item()) > F * code576.n // 4                              # random codewords, not the all-zero word
     dec.close(); enc.close()
+
+
+@pytest.mark.parametrize("name,algo", [("576x288", "-OMS"), ("576x288", "-NMS"), ("2304x1152", "-OMS")])
+def test_the_reference_simulator_itself_linked_against_this_library(built, name, algo):
+    """The reference's OWN simulator — code/gpu_fixed/main.cpp and every non-decoder source, unmodified, compiled where they lie by
+    oracle/Makefile — linked against libldpc_b200.so through oracle/ref_main_shim.cu in place of the reference's decoder .cu files.
+    One Eb/N0 point: the `SNR = ... | BER = ... | FER = ...` line it prints must agree with harness/ldpc_sim -gpu on the same point
+    within sampling error (the two draw different noise: cuRAND XORWOW seed 1234 there, counter-based Philox here)."""
+    exe = ROOT / "oracle" / "_ref" / f"ref_gpu_main_{name}"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_gpu_main_* not built (needs /root/reference at build time)")
+    ebn0 = 2.0
+    r = subprocess.run([str(exe), algo, "-min", str(ebn0), "-max", str(ebn0), "-iter", "10", "-fer", "600", "-n", "16384"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "libldpc_b200" in r.stdout and f"(II) Code LDPC (N, K)     : ({name.split('x')[0]}," in r.stdout
+    m = re.search(r"SNR = ([\d.]+) \| BER =\s+([\d.e+-]+) \| FER =\s+([\d.e+-]+) .*?MATRICES =\s*(\d+)\| FE = (\d+) \| BE = (\d+)", r.stdout)
+    assert m, r.stdout[-1500:]
+    frames, fe, be = int(m.group(4)), int(m.group(5)), int(m.group(6))
+    assert frames >= 65536 and fe >= 600 and abs(float(m.group(1)) - ebn0) < 1e-6
+    out, pts = run_sim("-fixed", "-gpu", algo, "1" if algo == "-OMS" else "0.75", "-iter", 10, "-min", ebn0, "-max", ebn0, "-fer", 600, "-code", name, "-frames", 65536, "-max-frames", 4 * 65536)
+    p = pts[ebn0]
+    fer_a, fer_b = fe / frames, p["fe"] / p["frames"]
+    sigma = (fer_a * (1 - fer_a) / frames + fer_b * (1 - fer_b) / p["frames"]) ** 0.5
+    assert abs(fer_a - fer_b) < 5 * sigma + 1e-4, (fer_a, fer_b, sigma)
+    ber_a, ber_b = float(m.group(2)), p["ber"]          # both count over the information part (ref: ber_analyzer/CErrorAnalyzer.cpp:119-159)
+    assert be > 0 and 0.4 < (ber_a + 1e-12) / (ber_b + 1e-12) < 2.5, (ber_a, ber_b)

@@ -115,13 +115,14 @@ def test_other_codes(built, name):
         assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 4, 4256])
+@pytest.mark.parametrize("kernel", [0, 1, 4, 4256, 4001])
 def test_dvbs2_long_code_frame_parallel(built, kernel):
     """DVB-S2 64800x32400 (a 32 399-deep chain in reference order) against the reference's own x86 decoder (golden fixture):
     plain frame-parallel kernel (1), bulk-copy-staged kernel (4), and whatever the library picks (0 -> 4)."""
     c = Code.load("64800x32400")
     gg = np.load(GOLD / "k4_64800x32400_x86sse.npz")
-    kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4000 else dict(kernel=kernel)      # 4256: kernel 4 with 256-consumer CTAs
+    # 4256: kernel 4 with 256-consumer CTAs; 4001: kernel 4 with one-dimensional bulk copies only (no tensor map, no gather4)
+    kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4100 else dict(kernel=4, fs_tma=1, fs_g4=1) if kernel == 4001 else dict(kernel=kernel)
     r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", **kw)
     assert r["kernel"] == (kw["kernel"] or 4)
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
@@ -175,10 +176,12 @@ def test_dvbs2_early_termination_staged_vs_plain_vs_oracle(built):
 def test_staged_kernel_all_semantics(code576, sem, algo):
     """kernel 4 on a batch that spans several CTAs and a ragged tail, every (semantics, algorithm) pair, stage ring depths 2..15"""
     llr = np.concatenate([awgn_llr(code576, 700, 2.0, 241), stress_llr(code576, 333, 243, full_range=(sem == "GPU_FIXED"))])
-    for iters, stages, nc in ((1, 0, 128), (10, 0, 128), (3, 2, 128), (3, 15, 128), (10, 0, 256), (3, 2, 256), (2, 9, 256)):
-        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, want_iters=True)
+    # tma / g4: 1 = one-dimensional bulk copies only, 2 = message lines through a 2-D tensor map / posterior lines through tile::gather4 (the defaults)
+    for iters, stages, nc, tma, g4 in ((1, 0, 128, 2, 2), (10, 0, 128, 2, 2), (3, 2, 128, 2, 2), (3, 15, 128, 2, 2), (10, 0, 256, 2, 2), (3, 2, 256, 2, 2), (2, 9, 256, 2, 2),
+                                       (10, 0, 128, 1, 1), (3, 2, 256, 1, 1), (3, 15, 128, 2, 1), (2, 9, 256, 1, 2), (10, 0, 128, 0, 0)):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=g4, want_iters=True)
         assert g["kernel"] == 4 and (g["iters"] == iters).all()
-        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"staged {sem}/{algo} I{iters} K{stages} NC{nc}")
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"staged {sem}/{algo} I{iters} K{stages} NC{nc} tma{tma} g4{g4}")
     if (sem, algo) in (("X86_SSE", "OMS"), ("GPU_FIXED", "2NMS")):        # several CTAs + a ragged tail
         big = np.concatenate([llr, llr[::-1], llr[:700]])                  # 2766 frames -> 692 words per row -> 6 CTAs of 128 consumers
         for nc in (128, 256):
@@ -187,8 +190,8 @@ def test_staged_kernel_all_semantics(code576, sem, algo):
     # per-frame early termination in the staged kernel (a second pass over the ring per iteration for the stop criterion): frames of
     # very different quality in one CTA, iteration counts, frozen state, several ring depths and both CTA widths
     mixed = np.concatenate([awgn_llr(code576, 300, 4.0, 245), awgn_llr(code576, 250, 0.0, 246), awgn_llr(code576, 477, 2.0, 247), stress_llr(code576, 40, 248, full_range=(sem == "GPU_FIXED"))])
-    for iters, stages, nc in ((10, 0, 128), (20, 2, 128), (7, 0, 256), (2, 9, 256), (3, 15, 128), (1, 0, 128)):
-        g = gpu_decode(code576, mixed, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, early_term=1, want_iters=True)
+    for iters, stages, nc, tma in ((10, 0, 128, 0), (20, 2, 128, 0), (7, 0, 256, 0), (2, 9, 256, 0), (3, 15, 128, 0), (1, 0, 128, 0), (10, 0, 128, 1), (7, 3, 256, 1)):
+        g = gpu_decode(code576, mixed, iters, algo=algo, semantics=sem, kernel=4, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, early_term=1, want_iters=True)
         o = oracle_decode(code576, g["prm"], mixed, iters)
         assert g["kernel"] == 4
         assert_same(g, o, f"staged ET {sem}/{algo} I{iters} K{stages} NC{nc}")
