@@ -173,6 +173,9 @@ int  ldpc_b200_decode(ldpc_handle h, const void* llr, uint8_t* hard, size_t fram
 int  ldpc_b200_decode_async(ldpc_handle h, int slot, const void* llr, uint8_t* hard, size_t frames, int iters, uint8_t* iters_done);
 int  ldpc_b200_sync(ldpc_handle h, int slot /* -1 = all */);
 int  ldpc_b200_host_alloc(void** p, size_t bytes);              /* pinned; ref: CUDA_MALLOC_HOST custom_cuda.cu:30-60, CTrame.cpp:38-41 */
+/* the same for buffers the host only WRITES and the GPU reads (LLR input): write-combined pinned memory — no cache snooping on the
+ * way to the device; reading it back on the CPU is slow.  Freed with ldpc_b200_host_free. */
+int  ldpc_b200_host_alloc_input(void** p, size_t bytes);
 int  ldpc_b200_host_free(void* p);
 /* device buffers for the device-resident entry points below, for C hosts that do not link the CUDA runtime themselves
  * (ref: CUDA_MALLOC_DEVICE code/gpu_fixed/custom_api/custom_cuda.cu:62-142).  Allocated on the handle's device. */

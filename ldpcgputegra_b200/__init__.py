@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
         "ldpc_b200_decode_async": (i32, [vp, i32, vp, vp, sz, i32, vp]),
         "ldpc_b200_sync": (i32, [vp, i32]),
         "ldpc_b200_host_alloc": (i32, [C.POINTER(vp), sz]),
+        "ldpc_b200_host_alloc_input": (i32, [C.POINTER(vp), sz]),
         "ldpc_b200_host_free": (i32, [vp]),
         "ldpc_b200_device_alloc": (i32, [vp, C.POINTER(vp), sz]),
         "ldpc_b200_device_free": (i32, [vp, vp]),
@@ -124,7 +125,7 @@ EXPORTS = ["ldpc_b200_abi_version", "ldpc_b200_device_count", "ldpc_b200_status_
            "ldpc_b200_load_code_header", "ldpc_b200_load_code_table", "ldpc_b200_save_code_table", "ldpc_b200_check_code",
            "ldpc_b200_free_code", "ldpc_b200_level_schedule", "ldpc_b200_create", "ldpc_b200_destroy", "ldpc_b200_last_error",
            "ldpc_b200_get_info", "ldpc_b200_quantize", "ldpc_b200_decode", "ldpc_b200_decode_async", "ldpc_b200_sync",
-           "ldpc_b200_host_alloc", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_stream", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
+           "ldpc_b200_host_alloc", "ldpc_b200_host_alloc_input", "ldpc_b200_host_free", "ldpc_b200_device_alloc", "ldpc_b200_device_free", "ldpc_b200_decode_device", "ldpc_b200_stream", "ldpc_b200_set_debug", "ldpc_b200_debug_state",
            "ldpc_b200_awgn_device", "ldpc_b200_awgn", "ldpc_b200_count_errors_device",
            "ldpc_b200_encoder_create", "ldpc_b200_encoder_destroy", "ldpc_b200_encoder_last_error", "ldpc_b200_encoder_info", "ldpc_b200_encode",
            "ldpc_b200_encode_device", "ldpc_b200_awgn_codeword_device", "ldpc_b200_count_errors_ref_device"]
@@ -241,10 +242,11 @@ def default_params(**kw) -> ParamsT:
 class PinnedArray:
     """numpy view over cudaMallocHost memory (ref: CTrame's pinned buffers, code/gpu_fixed/trame/CTrame.cpp:38-41)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined: bool = False):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         self._p = C.c_void_p()
-        _check(lib().ldpc_b200_host_alloc(C.byref(self._p), max(self.nbytes, 1)))
+        alloc = lib().ldpc_b200_host_alloc_input if write_combined else lib().ldpc_b200_host_alloc       # write-combined: input buffers the host only writes
+        _check(alloc(C.byref(self._p), max(self.nbytes, 1)))
         buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._p.value)
         self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 

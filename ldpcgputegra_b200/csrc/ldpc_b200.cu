@@ -974,6 +974,12 @@ int ldpc_b200_host_alloc(void** p, size_t bytes)
     if (ldpc_b200_device_count() <= 0) return LDPC_ERR_NO_DEVICE;
     return cudaMallocHost(p, bytes) == cudaSuccess ? LDPC_OK : LDPC_ERR_NOMEM;
 }
+int ldpc_b200_host_alloc_input(void** p, size_t bytes)
+{
+    if (!p) return LDPC_ERR_INVALID;
+    if (ldpc_b200_device_count() <= 0) return LDPC_ERR_NO_DEVICE;
+    return cudaHostAlloc(p, bytes, cudaHostAllocWriteCombined | cudaHostAllocPortable) == cudaSuccess ? LDPC_OK : LDPC_ERR_NOMEM;
+}
 int ldpc_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LDPC_OK : LDPC_ERR_CUDA; }
 
 int ldpc_b200_device_alloc(ldpc_handle h, void** p, size_t bytes)
