@@ -326,6 +326,9 @@ int build_rp_plan(ldpc_handle h, RpPlan& plan, size_t smem_budget)
     plan.pair_pad = pad_for(plan.P);
     plan.pair_pad_ok = plan.P > 1 && uniform && nr0 % 4 == 0;       // pad_for() really produced pitch = nrows (mod 32)
     plan.slots = slots_for(plan.G, plan.P, plan.pair_pad);
+    // experiment knob (tools/occupancy_sweep.py): fewer frame pairs per SM than shared memory allows, to measure what resident warps are
+    // worth to this kernel — the question behind a compressed message format ("compressed messages")
+    if (const char* cap = getenv("LDPC_B200_RP_MAX_SLOTS")) { const int c_ = atoi(cap); if (c_ >= 1) plan.slots = std::min(plan.slots, c_); }
     // static plan: uniform steps, every run specialised, at most one task per lane of a full group
     bool all_special = true;
     for (auto& r : plan.runs) all_special = all_special && r.variant != 0;
