@@ -33,6 +33,8 @@ namespace ldpcb200 {
 #define FS_PRODUCER_THREADS 64           // one warp fetches the posterior lines, one the message lines: a bulk copy costs ~46 issue cycles, and
                                          // the single producer of the first version (1340 cycles per row) bounded small batches
 #define FS_MAX_CONSUMERS 512
+#define FS_P2_BYTES 128u                   // tail of every stage: the row's edge words (<= FS_MAXDEG of them), written by the posterior-side producer
+#define FS_P2_OFFSET(A, NC) ((uint32_t)((A).msg_line0 + (A).max_deg) * (uint32_t)(NC) * 4u)
 #define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
 #define FS_MAXDEG 10                     // 1200x600, the gpu_fixed tree's default code (matrix/code.h:1), has rows of degree 9
 #define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
@@ -167,19 +169,19 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
     const uint32_t T4 = 4u * (uint32_t)A.T;
     uint32_t* const vt = A.V + t;
     uint32_t* mp = A.MSG + (e * (size_t)A.T + (size_t)t);
-    uint32_t p2[D], p2n[D];
-#pragma unroll
-    for (int j = 0; j < D; j++) p2[j] = __ldg(A.pos2 + e + j);
+    uint32_t p2[D];
     for (int r = 0; r < R; r++, e += D) {
-#pragma unroll
-        for (int j = 0; j < D; j++) p2n[j] = __ldg(A.pos2 + e + D + j);
         mbar_wait(bars + 8 * c.stage, c.phase);
-        fs_row<SEM, ALGO, D, FIRST, Q, NC, ET>(A, tid, vt, mp, T4, p2, ring + (uint32_t)c.stage * stage_bytes, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
+        const uint32_t st = ring + (uint32_t)c.stage * stage_bytes;
+        // the row's edge words: written behind the stage's lines by the producer that fetched them (round 2: the consumers' own
+        // row-ahead __ldg sat on the long scoreboard for 14 % of their samples once the producers had stopped being the bottleneck,
+        // profiles/r02_ncu_fs_small_v2.txt) — a broadcast shared-memory load behind the barrier they wait on anyway
+#pragma unroll
+        for (int j = 0; j < D; j++) p2[j] = lds_u32(st + FS_P2_OFFSET(A, NC) + 4u * j);
+        fs_row<SEM, ALGO, D, FIRST, Q, NC, ET>(A, tid, vt, mp, T4, p2, st, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
         mp = word_at(mp, (uint32_t)D, T4);
         c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
         if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
-#pragma unroll
-        for (int j = 0; j < D; j++) p2[j] = p2n[j];
     }
 }
 
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     const uint32_t bars = smem_u32(fs_smem);
     const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
     const uint32_t ring = fwd_s + FS_FWD * (uint32_t)A.max_deg * LINE;
-    const uint32_t stage_bytes = (uint32_t)(A.msg_line0 + A.max_deg) * LINE;
+    const uint32_t stage_bytes = (uint32_t)(A.msg_line0 + A.max_deg) * LINE + FS_P2_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * NC;
     if (threadIdx.x == 0) {
@@ -268,9 +270,11 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
                             const int Dn = (r + 1 < A.rows[c] || c + 1 >= A.nb_deg) ? D : A.deg[c + 1];
                             p2n = (idx_lane && j < Dn) ? __ldg(A.pos2 + e + D + j) : FS_F_HAZARD;
                         }
+                        const uint32_t p2_row = p2;                                         // with its flags: what the consumers need
                         if (sw == 1 && idx_lane && j < D) p2 &= ~FS_F_HAZARD;
                         if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
                         __syncwarp();
+                        if (idx_lane && j < D) sts_u32(ring + (uint32_t)stage * stage_bytes + FS_P2_OFFSET(A, NC) + 4u * j, p2_row);   // before lane 0's arrive (release) below
                         const bool want_msg = it > 0 || sw == 1;
                         const int groups = (D + 3) >> 2;                       // gather4: lane g < groups fetches edges 4g .. 4g+3 (the last one repeated to fill the group)
                         int r0 = 0, r1 = 0, r2 = 0, r3 = 0;

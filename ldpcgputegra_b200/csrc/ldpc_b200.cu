@@ -667,7 +667,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
             f.use_g4 = ok ? 1 : 0;
         }
         f.msg_line0 = f.use_g4 ? (f.max_deg + 3) / 4 * 4 : f.max_deg;
-        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.max_deg) * line, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
+        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.max_deg) * line + FS_P2_BYTES, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob

@@ -204,6 +204,26 @@ def test_staged_kernel_all_semantics(code576, sem, algo):
     assert np.array_equal(g["iters"], o["iters"]) and g["iters"].max() < 50
 
 
+@pytest.mark.parametrize("name,frames", [("576x288", 151552), ("4000x2000", 75776)])
+def test_staged_kernel_stress_against_plain_kernel(built, name, frames):
+    """Long-running cross-check of the staged kernel's ordering assumptions (generic-proxy stores -> proxy fence -> mbarrier ->
+    bulk / tensor-map copies of the same lines, the forwarded word written into a stage slot the copy engine refills): many
+    iterations, shallow and deep stage rings, every SM loaded with several CTAs, both producer paths — every posterior-derived
+    decision and every iteration count must equal the plain frame-parallel kernel's, which has no asynchronous copies at all."""
+    c = Code.load(name)
+    d1 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=1, semantics="ARM_SCALAR", early_term=1)
+    llr = d1.awgn(frames, pkg.sigma_for(1.6, 0.5), seed=77)
+    h1, it1 = d1.decode(llr, 40, want_iters=True)
+    d1.close()
+    for stages, nc, tma in ((2, 128, 2), (3, 256, 2), (0, 128, 2), (2, 256, 1), (0, 256, 1)):
+        d4 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=4, semantics="ARM_SCALAR", early_term=1, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, chunk_waves=1)
+        h4, it4 = d4.decode(llr, 40, want_iters=True)
+        d4.close()
+        assert np.array_equal(h4, h1), f"{name} K{stages} NC{nc} tma{tma}: {(h4 != h1).any(axis=1).sum()} frames differ"
+        assert np.array_equal(it4, it1), f"{name} K{stages} NC{nc} tma{tma}: iteration counts differ"
+    assert it1.min() < 40 and it1.max() == 40
+
+
 @pytest.mark.parametrize("kernel,name", [(4, "576x288"), (1, "576x288"), (4, "4000x2000")])
 def test_frame_parallel_batch_quartered_over_stream_slots(built, kernel, name):
     """decode() cuts a frame-parallel batch of >= 8192 frames into four chunks on the four stream slots (the chunks' kernels run
