@@ -76,6 +76,19 @@ def test_k7_int16_wide_rails_against_the_arm_scalar_reference(code576):
     assert g["W_1_2047_511_20_1_iters"].min() < 20
 
 
+@pytest.mark.parametrize("name", ["155x93", "2640x1320", "1920x960"])
+def test_k8_arm_tree_tables(built, name):
+    """The tables only the ARM tree carries, through its scalar decoder (fixture K8): oracle ARM_SCALAR == reference."""
+    c = Code.load(name)
+    g = np.load(GOLD / f"k8_{name}_armscalar.npz")
+    for key in [k[:-5] for k in g.files if k.endswith("_hard")]:
+        _, off, sv, sm, imax, early = key.split("_")
+        prm = default_params(algo="OMS", semantics="ARM_SCALAR", offset=int(off), sat_var=int(sv), sat_msg=int(sm), early_term=int(early))
+        o = oracle_decode(c, prm, g["llr"], int(imax))
+        assert np.array_equal(o["hard"], unpack(g[key + "_hard"], c.n)) and np.array_equal(o["iters"], g[key + "_iters"]), key
+        assert np.array_equal(o["post"], g[key + "_post"]) and np.array_equal(o["msgs"], g[key + "_msgs"]), key
+
+
 def test_live_reference_arm_wide_rails(code576):
     L = ref_arm("576x288")
     if L is None:

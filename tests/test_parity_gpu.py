@@ -265,6 +265,22 @@ def test_ragged_sizes_and_packed_output(code576, kernel):
     dec.close()
 
 
+@pytest.mark.parametrize("name", ["155x93", "2640x1320", "1920x960"])
+def test_arm_tree_tables_against_the_reference_scalar_decoder(built, name):
+    """The tables only the ARM tree carries (code/ldpc_decoder_arm/Constantes: the (155,64) Tanner code with N % 16 != 0, 2640x1320,
+    802.11e 1920x960) against fixture K8, minted from the ARM tree's scalar decoder: every int8 kernel that accepts the code, stop
+    criterion on (iteration counts) and off."""
+    c = Code.load(name)
+    g8 = np.load(GOLD / f"k8_{name}_armscalar.npz")
+    for key in [k[:-5] for k in g8.files if k.endswith("_hard")]:
+        _, off, sv, sm, imax, early = key.split("_")
+        for kernel in (0, 2, 1, 4) if c.n_checks >= 128 else (0, 2, 1):
+            r = gpu_decode(c, g8["llr"], int(imax), want_iters=True, algo="OMS", semantics="ARM_SCALAR", offset=int(off), sat_var=int(sv), sat_msg=int(sm),
+                           early_term=int(early), kernel=kernel)
+            assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), g8[key + "_hard"]), (key, kernel)
+            assert np.array_equal(r["post"], g8[key + "_post"]) and np.array_equal(r["msgs"], g8[key + "_msgs"]) and np.array_equal(r["iters"], g8[key + "_iters"]), (key, kernel, r["kernel"])
+
+
 def test_non_multiple_of_16_code_length(built):
     """N % 16 != 0 takes the scalar layout path in the reference (CDecoder_OMS_fixed_SSE.cpp:143-148); same here."""
     rng = np.random.default_rng(5)

@@ -5,6 +5,7 @@ The reference ships no golden vectors, so the fixtures under tests/
   K1/K2/K3  576x288  x86 SSE binary: OMS offset 1/2, NMS factor 29/24, I in {1,2,5,10}, AWGN @2 dB + saturating stress inputs
   K4        16 frames each of 1944x972, 2048x384, 2304x1152, 4000x2000, 64800x32400, I=10 (posteriors/messages as SHA-256 for the big ones)
   K5        ARM-tree scalar decoder with the stop criterion: per-frame iteration counts, I_max in {10,30}, 1..3 dB
+  K8        the ARM tree's own tables (155x93, 2640x1320, 1920x960) through its scalar decoder, stop criterion on and off
   K7        ARM-tree scalar decoder at rails beyond int8 (+-2047/+-511, +-32767/+-8191, +-300/+-300): pins the int16 storage path
 Run in the container that has /root/reference; the GPU box and CI only read the .npz files.
 """
@@ -68,8 +69,30 @@ def mint_k7():
     np.savez_compressed(OUT / "k7_576x288_armscalar_wide.npz", **out)
 
 
+def mint_k8():
+    """K8: the tables only the ARM tree carries (155x93 — N % 16 != 0 —, 2640x1320, 802.11e 1920x960) through the ARM tree's scalar decoder
+    with its stop criterion: hard decisions, posteriors, messages, per-frame iteration counts (code/ldpc_decoder_arm/Constantes/*)."""
+    for name in ("155x93", "2640x1320", "1920x960"):
+        c = Code.load(name)
+        La = ref_arm(name)
+        assert La is not None, f"oracle/_ref/libref_arm_{name}.so missing (make -C oracle ref)"
+        llr = np.concatenate([awgn_llr(c, 24, 2.5, 801), awgn_llr(c, 16, 4.0, 802), stress_llr(c, 8, 803)])
+        out = {"llr": llr}
+        for (off, sv, sm, imax, early) in [(1, 127, 31, 20, True), (1, 127, 31, 10, False)]:
+            r = ref_arm_decode(La, c, off, sv, sm, early, llr, imax)
+            key = f"A_{off}_{sv}_{sm}_{imax}_{int(early)}"
+            out[key + "_hard"] = np.packbits(r["hard"], axis=1, bitorder="little")
+            out[key + "_iters"] = r["iters"]
+            out[key + "_post"] = r["post"].astype(np.int8); out[key + "_msgs"] = r["msgs"].astype(np.int8)
+            print(name, key, "iterations", int(r["iters"].min()), "..", int(r["iters"].max()))
+        np.savez_compressed(OUT / f"k8_{name}_armscalar.npz", **out)
+
+
 def main():
     OUT.mkdir(exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "k8":
+        mint_k8()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "k7":
         mint_k7()
         return
@@ -106,6 +129,7 @@ def main():
             out[key + "_post"] = r["post"].astype(np.int8); out[key + "_msgs"] = r["msgs"].astype(np.int8)
     np.savez_compressed(OUT / "k5_576x288_armscalar_et.npz", **out)
     mint_k7()
+    mint_k8()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

@@ -17,6 +17,10 @@ X86 = {"576x288": "576x288", "1944x972": "1944x972", "2048x384": "2048x384", "23
        "64800x32400": "64800x32400.dvb-s2", "64800x7200": "64800x7200.dvb-s2", "64800x6480": "64800x6480.dvb-s2"}
 
 
+# tables that only the ARM tree carries (code/ldpc_decoder_arm/Constantes; SURVEY App. C last row)
+ARM_ONLY = {"155x93": "155x93", "2640x1320": "2640x1320", "1920x960": "802.11e.1920x960"}
+
+
 def load_gpu(d: Path):
     """gpu_fixed flavour: macros in constantes_gpu.h + table in constantes_decoder.h; a few dirs only carry an x86-style header."""
     if (d / "constantes_decoder.h").exists():
@@ -46,6 +50,8 @@ def main():
                 g.save(CODES_DIR / f"{name}.gpu.ldpc")
         else:
             done[name] = g
+    for name, d in ARM_ONLY.items():
+        done[name] = Code.from_header(REF / "ldpc_decoder_arm/Constantes" / d / "constantes_sse.h")
     for name, c in done.items():
         c.save(CODES_DIR / f"{name}.ldpc")
         lv, _ = c.level_schedule()
