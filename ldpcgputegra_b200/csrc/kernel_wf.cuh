@@ -24,7 +24,6 @@
 namespace ldpcb200 {
 
 #define WF_MAX_WARPS 24            // warps (= frames in flight) per CTA: 768 threads leave 85 registers per thread
-#define WF_IDX_NONE 0xFFFFu
 
 struct WfRun {             // 16 bytes, read as one 128-bit shared load: consecutive 32-row steps of ONE degree class (and, layered, one level)
     uint16_t deg, cls;     // row degree, degree class

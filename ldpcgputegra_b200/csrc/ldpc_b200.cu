@@ -940,6 +940,7 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     size_t k = h->kernel == 2 ? 1 : (h->kernel == 5 || h->kernel == 6) ? std::max<size_t>(1, h->max_frames / 8 / wave) : std::max<size_t>(1, (h->max_frames / 4 + wave / 2) / wave);
     if (h->prm.reserved[2] > 0) k = (size_t)h->prm.reserved[2];
     h->chunk_frames = std::max<size_t>(std::min<size_t>(h->max_frames, k * wave), 1);
+    if (const char* cf = getenv("LDPC_B200_CHUNK_FRAMES")) { const long v = atol(cf); if (v > 0) h->chunk_frames = (size_t)v; }     // experiment knob (tools/e2e_chunks.py)
     // frame-parallel kernels: a wave is 300 Ki frames, so the rule above never split a batch and decode() ran H2D, kernel and D2H
     // back to back.  Quarter the batch over the four stream slots instead (the chunks' kernels share the SMs: a 32 Ki-frame chunk
     // is 64 CTAs), unless reserved[2] says otherwise.
@@ -1059,10 +1060,14 @@ int ldpc_b200_decode(ldpc_handle h, const void* llr, uint8_t* hard, size_t frame
         for (int s = 0; s < kSlots && (size_t)s < nchunks && !h->debug; s++)
             if ((rc = reserve_slot(h, h->slot[s], first, iters_done != nullptr))) return rc;
     }
+    // Uniform chunks of one kernel wave.  Measured alternatives (profiles/r02_e2e_chunks.jsonl, r02_e2e_ramp.jsonl): smaller chunks lose to
+    // per-chunk host work (half a wave 16.8 against 18.4 Gb/s), larger ones to the pipeline's fill and drain, and a ramped schedule
+    // (quarter and half chunks at both ends) changes nothing — what separates the call from the host link's rate is a fixed ~0.17 ms.
     for (size_t f = 0; f < frames && rc == LDPC_OK; f += chunk, k++) {
         const size_t cnt = std::min(chunk, frames - f);
         const int slot = h->debug ? 0 : (k % kSlots);
-        if (k >= kSlots) CU_TRY(h, cudaStreamSynchronize(h->slot[slot].stream));   // slot buffers are reused
+        // A slot's device buffers are reused by chunk k + kSlots on the SAME stream, i.e. in order behind chunk k's copy out: no host
+        // synchronisation is needed for that, and not blocking here lets the host queue the whole batch ahead of the copy engines.
         rc = ldpc_b200_decode_async(h, slot, (const int8_t*)llr + f * n * (size_t)h->elem, hard + f * hb, cnt, iters, iters_done ? iters_done + f : nullptr);
     }
     int rc2 = ldpc_b200_sync(h, -1);
