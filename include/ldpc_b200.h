@@ -118,7 +118,10 @@ typedef struct {
                              [0],[1] = (warps, pairs) of an on-chip group; [2] = kernel waves per pipeline chunk of decode();
                              [3] = 1: descriptor-driven on-chip plan, 3: 32-row steps, 5: pair-slowest lane mapping;
                              [4] = stage-ring depth of the staged kernel (bits 0..7) | its CTA width (bits 8..11: 1 = 128, 2 = 256 consumer threads)
-                                   | message lines through a TMA tensor map (bits 12..13: 1 = never, 2 = always) */
+                                   | message lines through a TMA tensor map (bits 12..13: 1 = never, 2 = always)
+                                   | posterior lines through tile::gather4 (bits 14..15, likewise)
+                                   | compressed messages, four words per row instead of one per edge (bits 16..17: 2 = on, rows of degree <= 8;
+                                     bit-exact, 2/3 of the state, measured slightly SLOWER: off unless asked for — DESIGN.md 3.2b) */
 } ldpc_params_t;
 
 typedef struct ldpc_b200_handle_s* ldpc_handle;

@@ -117,4 +117,29 @@ __global__ void fp_debug_state_kernel(const uint32_t* __restrict__ V, const uint
     }
 }
 
+// the same for the staged kernel's COMPRESSED messages (kernel_fp.cuh: fp_row_math_c; four words per row and thread): every edge's
+// message is re-expanded, so ldpc_b200_debug_state returns the bytes the uncompressed kernels hold.  edge_row[e] = row << 4 | slot.
+__global__ void fc_debug_state_kernel(const uint32_t* __restrict__ V, const uint32_t* __restrict__ MSGC, const uint32_t* __restrict__ edge_row,
+                                      int8_t* post, int8_t* msgs, size_t frames, int n, int m, int T, int lo, int have_msgs)
+{
+    const size_t total = frames * (size_t)(n + m);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / (size_t)(n + m);
+        const int k = (int)(i % (size_t)(n + m));
+        const int t = (int)(f >> 2), b = (int)(f & 3);
+        if (k < n) { if (post) post[f * n + k] = (int8_t)((int)((V[(size_t)k * T + t] >> (8 * b)) & 0xFF) + lo); }
+        else if (msgs) {
+            const int e = k - n;
+            int v = 0;
+            if (have_msgs) {
+                const uint32_t er = edge_row[e], row = er >> 4, j = er & 15u, g = (uint32_t)b >> 1, sh = 16u * ((uint32_t)b & 1u);
+                const uint32_t cw = (MSGC[(size_t)(4 * row + g) * T + t] >> sh) & 0xFFFFu, es = (MSGC[(size_t)(4 * row + 2 + g) * T + t] >> sh) & 0xFFFFu;
+                const int mag = (int)(((es >> j) & 1u) ? (cw >> 8) : (cw & 0xFFu));
+                v = ((es >> (8 + j)) & 1u) ? -mag : mag;
+            }
+            msgs[f * (size_t)m + e] = (int8_t)v;
+        }
+    }
+}
+
 }  // namespace ldpcb200

@@ -1,0 +1,19 @@
+// inst_fc_gpu.cu — instantiations of the bulk-copy-staged frame-parallel kernel on COMPRESSED messages (kernel_fs.cuh, CMP = true) for semantics mode LDPC_SEM_GPU_FIXED: its own
+// translation unit so that the staged kernel's 6 variants per (semantics, algorithm) compile beside the on-chip kernel's (see launch.cuh)
+#define LDPC_INST_SEM LDPC_SEM_GPU_FIXED
+#include "launch.cuh"
+
+namespace ldpcb200 {
+
+int launch_fc_gpu(int algo, const FsArgs& args, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (algo) {
+    case LDPC_ALGO_MS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_MS, true>(args, blocks, smem, st);
+    case LDPC_ALGO_OMS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_OMS, true>(args, blocks, smem, st);
+    case LDPC_ALGO_NMS:
+    case LDPC_ALGO_2NMS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_NMS, true>(args, blocks, smem, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace ldpcb200

@@ -76,6 +76,83 @@ __device__ __forceinline__ void fp_row_math(const uint32_t (&wv)[D], const uint3
     }
 }
 
+// ---- the same row on COMPRESSED messages (staged kernel, rows of degree <= 8) ------------------------------------------
+// A min-sum row sends only two magnitudes: c1 to the edge(s) that held the minimum, c2 to the others, each with its own sign.  The row's
+// D message words are therefore stored as FOUR words per row and thread (4 frames), whatever D:
+//     cm[g]     (g = frame pair 0 | 1)  bytes { c1 frame 2g, c2 frame 2g, c1 frame 2g+1, c2 frame 2g+1 }
+//     cm[2 + g]                         halves: bits 0..7 = "edge j gets c2" (the d of pass 2), bits 8..15 = "message j is negative"
+// Re-expansion of edge j is a shift that brings both of its bits to bit 7 / bit 15 of the half, a sign-replicating PRMT (the c2 mask),
+// a bit select and the sign xor — all exact, the expanded message is the word the uncompressed kernel would have loaded (a zero
+// magnitude may carry a sign: -0 adds like +0).  Packing costs three FMA-pipe operations per edge: the bits are ACCUMULATED as
+// subnormal binary16 numbers (bit j of a half = 2^(j-24); d and the sign indicator are 0.0 / 1.0, the sums stay below 2^-16: exact).
+template <int SEM, int ALGO, int D, bool FIRST, bool Q>
+__device__ __forceinline__ void fp_expand_pair(uint32_t cw, uint32_t es, const RowConsts& K, h2 (&nM)[D])
+{
+    const h2 inv256 = h2_const(1.0f / 256.0f), m4 = h2_const(-4.0f);
+    const uint32_t c1q = h2_bits(__hfma2(bits_h2(__byte_perm(cw, K.c64, 0x4240)), inv256, m4));       // c1/256 per half
+    const uint32_t c2q = h2_bits(__hfma2(bits_h2(__byte_perm(cw, K.c64, 0x4341)), inv256, m4));
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const uint32_t x = es << (7 - j);
+        uint32_t mask;                                                       // 0xFFFF per half where bit 7 of its low byte is set
+        asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(mask) : "r"(x));           // selector msb = replicate the byte's sign
+        const uint32_t mag = (c2q & mask) | (c1q & ~mask);
+        nM[j] = __hsub2(m4, bits_h2(and_xor(x, 0x80008000u, mag)));          // -(message)/256 - 4
+    }
+}
+
+template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
+__device__ __forceinline__ void fp_row_math_c(const uint32_t (&wv)[D], const uint32_t (&cm)[4], const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi,
+                                              uint32_t (&nv)[D], uint32_t (&ncm)[4])
+{
+    static_assert(D <= 8, "compressed rows carry 8 edge bits per frame");
+    uint32_t ov[2][D];
+    const h2 inv256 = h2_const(1.0f / 256.0f), m4 = h2_const(-4.0f);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        h2 xu[D], a[D], nM[D];
+        uint32_t f[D];
+        if (!FIRST) fp_expand_pair<SEM, ALGO, D, FIRST, Q>(cm[g], cm[2 + g], K, nM);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const h2 wU = g ? bytes23_to_w(wv[j], K.c64) : bytes01_to_w(wv[j], K.c64);
+            xu[j] = __hmin2(__hfma2_sat(wU, inv256, FIRST ? m4 : nM[j]), K.top);
+        }
+        RowState s;
+        row_pass1<SEM, ALGO, Q, D>(xu, a, f, s, K);
+        RowOut o; row_finish<SEM, ALGO>(s, D, K, K.msg_c, o);
+        RowOutS q; fold_sign(o, q);
+        h2 accd = bits_h2(0u), accs = bits_h2(0u);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const h2 d = __hfma2_sat(a[j], K.k256, q.nmin1);                 // 0 where a == min1, 1 elsewhere
+            const h2 smag = __hfma2(d, q.sdc, q.sc1);
+            const h2 msg = bits_h2(and_xor(f[j], 0x80008000u, h2_bits(smag)));
+            const h2 unew = __hmin2(__hadd2_sat(xu[j], msg), K.top);
+            ov[g][j] = q_to_w(unew, 0.0f);
+            const h2 bit = bits_h2(0x00010001u << j);                        // 2^(j-24) per half
+            accd = __hfma2(d, bit, accd);
+            accs = __hfma2(__hmul2_sat(msg, h2_const(-256.0f)), bit, accs);   // |message| >= 1/256 or zero: 1 where negative, else 0
+        }
+        uint32_t cw = __byte_perm(q_to_w(o.c1, 0.0f), q_to_w(__hadd2(o.c1, o.dc), 0.0f), 0x6240);
+        uint32_t es = __byte_perm(h2_bits(accd), h2_bits(accs), 0x6240);
+        if (ET && !FIRST) {   // frozen frames keep their state
+            const uint32_t keep = g ? keep_hi : keep_lo;
+            cw = (cm[g] & keep) | (cw & ~keep);
+            es = (cm[2 + g] & keep) | (es & ~keep);
+        }
+        ncm[g] = cw; ncm[2 + g] = es;
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        nv[j] = pack_bytes(ov[0][j], ov[1][j]);
+        if (ET) {
+            const uint32_t keep = __byte_perm(keep_lo, keep_hi, 0x6420);
+            nv[j] = (wv[j] & keep) | (nv[j] & ~keep);
+        }
+    }
+}
+
 // ---- one row, degree known at compile time, x kept in registers --------------------------------------------------
 template <int SEM, int ALGO, int D, bool FIRST, bool ET, bool Q>
 __device__ __forceinline__ void fp_row(const FpArgs& A, int t, size_t e, const RowConsts& K, uint32_t keep_lo, uint32_t keep_hi)

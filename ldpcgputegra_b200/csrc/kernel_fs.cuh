@@ -34,7 +34,7 @@ namespace ldpcb200 {
                                          // the single producer of the first version (1340 cycles per row) bounded small batches
 #define FS_MAX_CONSUMERS 512
 #define FS_P2_BYTES 128u                   // tail of every stage: the row's edge words (<= FS_MAXDEG of them), written by the posterior-side producer
-#define FS_P2_OFFSET(A, NC) ((uint32_t)((A).msg_line0 + (A).max_deg) * (uint32_t)(NC) * 4u)
+#define FS_P2_OFFSET(A, NC) ((uint32_t)((A).msg_line0 + (A).msg_lines) * (uint32_t)(NC) * 4u)
 #define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
 #define FS_MAXDEG 10                     // 1200x600, the gpu_fixed tree's default code (matrix/code.h:1), has rows of degree 9
 #define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
@@ -63,6 +63,8 @@ struct FsArgs {
     int use_tm;              // the message lines of a row arrive as ONE 2-D tensor copy (box = nc words x row degree over MSG[m][T])
     int use_g4;              // the posterior lines arrive four at a time (tile::gather4 over V[n][T]); hazard lines come along and are ignored
     int msg_line0;           // first message line of a stage: max_deg, or max_deg rounded up to 4 with gather4 (it writes whole groups of four)
+    int cmp;                 // compressed messages (the CMP instantiation, rows of degree <= 8): MSG is [4 * rows][T], four words per row and thread
+    int msg_lines;           // message lines of a stage: max_deg, or 4 when compressed
     ldpc_params_t prm;
     alignas(64) CUtensorMap tm_msg[LDPC_MAX_DEG_CLASSES];    // one map per degree class: the box height is part of the map
     alignas(64) CUtensorMap tm_v;                            // gather4: box = nc words x 1 row
@@ -103,12 +105,13 @@ __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence
 // thread's own earlier stores
 // The stage of the PREVIOUS row is handed back here, between this row's arithmetic and its stores: the fence then only has
 // to cover stores that were issued a whole row ago, so it never waits on fresh ones.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET>
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP>
 __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, const uint32_t (&p2)[D], uint32_t stage_s, const RowConsts& K,
                                        uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool fwd_ok, uint32_t keep_lo, uint32_t keep_hi)
 {
     constexpr uint32_t LINE = NC * 4u;
-    uint32_t wv[D], wm[D], nv[D], nm[D];
+    constexpr int ML = CMP ? 4 : D;                // message words per row and thread (kernel_fp.cuh: fp_row_math_c)
+    uint32_t wv[D], wm[ML], nv[D], nm[ML];
     // Hazards (edges the producer did not prefetch because one of the last FS_HAZARD rows wrote the variable).  The common pattern —
     // exactly one such edge per row, its writer at most FS_FWD rows back: the staircase of DVB-S2 and of every IRA code — is
     // served by copying the writer's word from the forwarding ring INTO the stage slot (shared memory takes a run-time slot
@@ -142,16 +145,21 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, u
         }
     }
 #pragma unroll
-    for (int j = 0; j < D; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.msg_line0 + j) * LINE + 4 * tid);
-    fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);        // ET: frozen frames keep their state
+    for (int j = 0; j < ML; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.msg_line0 + j) * LINE + 4 * tid);
+    if constexpr (CMP) fp_row_math_c<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);
+    else fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);   // ET: frozen frames keep their state
     fence_proxy_async_global();                    // the previous rows' stores, before any later bulk copy of the same lines
     __syncwarp();
     if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        *word_at(vt, p2[j] & FS_IDX_MASK, T4) = nv[j];          // vt = V + t, mp = MSG + e * T + t, T4 = 4 * T
-        *word_at(mp, (uint32_t)j, T4) = nm[j];
+        *word_at(vt, p2[j] & FS_IDX_MASK, T4) = nv[j];          // vt = V + t, mp = MSG + (first message line of the row) * T + t, T4 = 4 * T
+        if (!CMP) *word_at(mp, (uint32_t)j, T4) = nm[j];
         sts_u32(fwd_s + (((q & (FS_FWD - 1)) * (uint32_t)A.max_deg + j) * NC + tid) * 4u, nv[j]);
+    }
+    if (CMP) {
+#pragma unroll
+        for (int j = 0; j < ML; j++) *word_at(mp, (uint32_t)j, T4) = nm[j];
     }
 }
 
@@ -162,14 +170,15 @@ struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 // global memory (L1 hit for 3 rows out of 4, L2 otherwise) and used to sit at the head of every row's dependency chain
 // (profiles/r01_ncu_fs_v2.txt: 15 % of the stall samples on the long scoreboard).  pos2 is padded by FS_MAXDEG words so that the
 // read past the last row is harmless; the words fetched across a class boundary are simply dropped.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET>
-__device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP>
+__device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, size_t& rho, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
                                          uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c, uint32_t keep_lo, uint32_t keep_hi)
 {
     const uint32_t T4 = 4u * (uint32_t)A.T;
     uint32_t* const vt = A.V + t;
-    uint32_t* mp = A.MSG + (e * (size_t)A.T + (size_t)t);
+    uint32_t* mp = A.MSG + ((CMP ? 4 * rho : e) * (size_t)A.T + (size_t)t);
     uint32_t p2[D];
+    rho += (size_t)R;
     for (int r = 0; r < R; r++, e += D) {
         mbar_wait(bars + 8 * c.stage, c.phase);
         const uint32_t st = ring + (uint32_t)c.stage * stage_bytes;
@@ -178,8 +187,8 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
         // profiles/r02_ncu_fs_small_v2.txt) — a broadcast shared-memory load behind the barrier they wait on anyway
 #pragma unroll
         for (int j = 0; j < D; j++) p2[j] = lds_u32(st + FS_P2_OFFSET(A, NC) + 4u * j);
-        fs_row<SEM, ALGO, D, FIRST, Q, NC, ET>(A, tid, vt, mp, T4, p2, st, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
-        mp = word_at(mp, (uint32_t)D, T4);
+        fs_row<SEM, ALGO, D, FIRST, Q, NC, ET, CMP>(A, tid, vt, mp, T4, p2, st, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
+        mp = word_at(mp, (uint32_t)(CMP ? 4 : D), T4);
         c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
         if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
     }
@@ -189,7 +198,7 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
 // this time (nothing is written, so nothing can be stale once the update pass has drained) — and per row the parity of (x > 0),
 // x = sat(v - m) with the updated messages (ref: code/ldpc_decoder_arm/CDecoder/OMS/CDecoder_OMS_fixed_x86.cpp:150-178; the same
 // words as fp_syndrome in kernel_fp.cuh).  Returns bit15-of-each-half words: 1 = a check of that frame failed.
-template <int NC>
+template <int NC, bool CMP>
 __device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int lane, const RowConsts& K, int lo, uint32_t bars, uint32_t ring, uint32_t stage_bytes,
                                                   int Kst, FsCursor& c, uint32_t& bad_lo, uint32_t& bad_hi)
 {
@@ -203,6 +212,34 @@ __device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int 
             mbar_wait(bars + 8 * c.stage, c.phase);
             const uint32_t st = ring + (uint32_t)c.stage * stage_bytes + 4u * (uint32_t)tid;
             uint32_t p0 = dpar, p1 = dpar;
+            if constexpr (CMP) {
+                // the row's four words re-expanded edge by edge (fp_expand_pair in kernel_fp.cuh, with a run-time degree)
+                const h2 m4 = h2_const(-4.0f);
+                uint32_t c1q[2], c2q[2], es[2];
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t cw = lds_u32(st + (A.msg_line0 + g) * LINE);
+                    es[g] = lds_u32(st + (A.msg_line0 + 2 + g) * LINE) << (8 - D);           // edge 0's bits at bit 7 / bit 15 after one more shift
+                    c1q[g] = h2_bits(__hfma2(bits_h2(__byte_perm(cw, K.c64, 0x4240)), inv256, m4));
+                    c2q[g] = h2_bits(__hfma2(bits_h2(__byte_perm(cw, K.c64, 0x4341)), inv256, m4));
+                }
+                for (int j = D - 1; j >= 0; j--) {               // parity is order-free: walk the edges from the last, whose bits are in place first
+                    const uint32_t wv = lds_u32(st + j * LINE);
+                    h2 x[2];
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        const uint32_t xs = es[g];
+                        es[g] <<= 1;
+                        uint32_t mask;
+                        asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(mask) : "r"(xs));
+                        const uint32_t mag = (c2q[g] & mask) | (c1q[g] & ~mask);
+                        const h2 nM = __hsub2(m4, bits_h2(and_xor(xs, 0x80008000u, mag)));
+                        x[g] = __hmin2(__hfma2_sat(g ? bytes23_to_w(wv, K.c64) : bytes01_to_w(wv, K.c64), inv256, nM), K.top);
+                    }
+                    p0 ^= h2_bits(__hadd2(x[0], lo_np));
+                    p1 ^= h2_bits(__hadd2(x[1], lo_np));
+                }
+            } else
             for (int j = 0; j < D; j++) {
                 const uint32_t wv = lds_u32(st + j * LINE), wm = lds_u32(st + (A.msg_line0 + j) * LINE);
                 const h2 x0 = __hmin2(__hfma2_sat(bytes01_to_w(wv, K.c64), inv256, __hfma2(bytes01_to_w(wm, K.c64), __hneg2(inv256), half)), K.top);
@@ -222,7 +259,7 @@ __device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int 
 
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
-template <int SEM, int ALGO, int NC, int MAXD, bool ET>
+template <int SEM, int ALGO, int NC, int MAXD, bool ET, bool CMP = false>
 __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
@@ -232,7 +269,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     const uint32_t bars = smem_u32(fs_smem);
     const uint32_t fwd_s = bars + (uint32_t)((16 * Kst + 127) / 128 * 128);
     const uint32_t ring = fwd_s + FS_FWD * (uint32_t)A.max_deg * LINE;
-    const uint32_t stage_bytes = (uint32_t)(A.msg_line0 + A.max_deg) * LINE + FS_P2_BYTES;
+    const uint32_t stage_bytes = (uint32_t)(A.msg_line0 + A.msg_lines) * LINE + FS_P2_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * NC;
     if (threadIdx.x == 0) {
@@ -260,11 +297,11 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
         for (int it = 0; it < A.iters; it++) {
             const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
             for (int sw = 0; sw < sweeps; sw++) {
-                size_t e = 0;
+                size_t e = 0, rho = 0;                               // first edge / number of the row
                 uint32_t p2n = (idx_lane && j < A.deg[0]) ? __ldg(A.pos2 + j) : FS_F_HAZARD;
                 for (int c = 0; c < A.nb_deg; c++) {
                     const int D = A.deg[c];
-                    for (int r = 0; r < A.rows[c]; r++, e += D) {
+                    for (int r = 0; r < A.rows[c]; r++, e += D, rho++) {
                         uint32_t p2 = (idx_lane && j < D) ? p2n : FS_F_HAZARD;
                         {   // next row in memory order: same class, or the first row of the next class
                             const int Dn = (r + 1 < A.rows[c] || c + 1 >= A.nb_deg) ? D : A.deg[c + 1];
@@ -283,14 +320,16 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
                             r0 = (int)(__shfl_sync(0xFFFFFFFFu, p2, b) & FS_IDX_MASK); r1 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 1, D - 1)) & FS_IDX_MASK);
                             r2 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 2, D - 1)) & FS_IDX_MASK); r3 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 3, D - 1)) & FS_IDX_MASK);
                         }
-                        const bool go = msg_side ? (mine && want_msg && (A.use_tm ? lane == 0 : j < D)) : (A.use_g4 ? lane < groups : !(p2 & FS_F_HAZARD));
+                        const int ML = CMP ? 4 : D;                             // message lines of this row
+                        const size_t ml0 = CMP ? 4 * rho : e;                   // its first line in MSG
+                        const bool go = msg_side ? (mine && want_msg && (A.use_tm ? lane == 0 : j < ML)) : (A.use_g4 ? lane < groups : !(p2 & FS_F_HAZARD));
                         const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
                         const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
-                        if (lane == 0) mbar_arrive_expect_tx(full, ((msg_side && A.use_tm) ? (want_msg ? (uint32_t)D : 0u) : (!msg_side && A.use_g4) ? 4u * n_lines : n_lines) * LINE);
+                        if (lane == 0) mbar_arrive_expect_tx(full, ((msg_side && A.use_tm) ? (want_msg ? (uint32_t)ML : 0u) : (!msg_side && A.use_g4) ? 4u * n_lines : n_lines) * LINE);
                         __syncwarp();
                         if (go) {
-                            if (msg_side && A.use_tm) tma_g2s_2d(dst0 + A.msg_line0 * LINE, &A.tm_msg[c], t0, (int)e, full);
-                            else if (msg_side) bulk_g2s(dst0 + (A.msg_line0 + j) * LINE, A.MSG + ((e + j) * A.T + t0), LINE, full);
+                            if (msg_side && A.use_tm) tma_g2s_2d(dst0 + A.msg_line0 * LINE, &A.tm_msg[CMP ? 0 : c], t0, (int)ml0, full);
+                            else if (msg_side) bulk_g2s(dst0 + (A.msg_line0 + j) * LINE, A.MSG + ((ml0 + j) * A.T + t0), LINE, full);
                             else if (A.use_g4) tma_gather4(dst0 + 4u * (uint32_t)lane * LINE, &A.tm_v, t0, r0, r1, r2, r3, full);
                             else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
                         }
@@ -315,13 +354,13 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     uint32_t done[4] = { 0u, 0u, 0u, 0u };
     int it = 0;
     for (; it < A.iters; it++) {
-        size_t e = 0;
+        size_t e = 0, rho = 0;
         for (int c = 0; c < A.nb_deg; c++) {
             const int D = A.deg[c], R = A.rows[c];
             const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
             // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
             K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
-#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET>(A, tid, t, e, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
+#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET, CMP>(A, tid, t, e, rho, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
 #define FS_CASE(DD)                                                                          \
     case DD:                                                                                 \
         if constexpr (DD <= MAXD) {                                                          \
@@ -338,7 +377,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
             fence_proxy_async_global();                // ... and visible to the producers' bulk copies of the stop-criterion pass
             __syncthreads();
             uint32_t b0, b1;
-            fs_syndrome_sweep<NC>(A, tid, lane, K, lo, bars, ring, stage_bytes, Kst, cur, b0, b1);
+            fs_syndrome_sweep<NC, CMP>(A, tid, lane, K, lo, bars, ring, stage_bytes, Kst, cur, b0, b1);
             // frames that pass now and were not frozen before stop at iteration it + 1 (same bookkeeping as fp_decode_kernel)
             const uint32_t pass_lo = ~b0 & 0x80008000u, pass_hi = ~b1 & 0x80008000u;
             if ((pass_lo & 0x00008000u) && !done[0]) done[0] = it + 1;

@@ -21,6 +21,10 @@ int launch_fs_x86(int, const FsArgs&, int, size_t, cudaStream_t);
 int launch_fs_uniform(int, const FsArgs&, int, size_t, cudaStream_t);
 int launch_fs_arm(int, const FsArgs&, int, size_t, cudaStream_t);
 int launch_fs_gpu(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fc_x86(int, const FsArgs&, int, size_t, cudaStream_t);        // the same kernel on compressed messages (inst_fc_*.cu)
+int launch_fc_uniform(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fc_arm(int, const FsArgs&, int, size_t, cudaStream_t);
+int launch_fc_gpu(int, const FsArgs&, int, size_t, cudaStream_t);
 int launch_rp_x86(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
 int launch_rp_uniform(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
 int launch_rp_arm(int, int, const RpArgs&, int, int, size_t, cudaStream_t);
@@ -48,23 +52,24 @@ static int do_rp(const RpArgs& a, int blocks, int threads, size_t smem, cudaStre
     }
     return (int)cudaGetLastError();
 }
-template <int SEM, int ALGO>
+template <int SEM, int ALGO, bool CMP = false>
 static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
 {
 #define FS_LAUNCH(NCV, MD, ETV)                                                                                                              \
-    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV, MD, ETV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, NCV, MD, ETV, CMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return (int)e;                                                                                                      \
-      fs_decode_kernel<SEM, ALGO, NCV, MD, ETV><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
+      fs_decode_kernel<SEM, ALGO, NCV, MD, ETV, CMP><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
+    if (CMP && a.max_deg > 8) return (int)cudaErrorInvalidValue;        // compressed rows carry 8 edge bits per frame
     // CTA width x widest row body x early termination.  The kernel's registers are those of its widest body, and the two producer
     // warps get the same allocation as the consumers: 256 consumers per CTA keep 16 consumer warps on an SM where 128 keep 12
     // (DESIGN.md 3.2b).  320 consumers capped at 80 registers (20 consumer warps) were measured 3 % SLOWER at a balanced batch and
     // the degree-10 body needs 120 registers (one wide CTA per SM, never a win): neither is instantiated.
     if (a.et) {
         if (a.nc == 256 && a.max_deg <= 8) FS_LAUNCH(256, 8, true)
-        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, true) else FS_LAUNCH(128, FS_MAXDEG, true) }
+        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, true) else if constexpr (!CMP) FS_LAUNCH(128, FS_MAXDEG, true) }
     } else {
         if (a.nc == 256 && a.max_deg <= 8) FS_LAUNCH(256, 8, false)
-        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, false) else FS_LAUNCH(128, FS_MAXDEG, false) }
+        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, false) else if constexpr (!CMP) FS_LAUNCH(128, FS_MAXDEG, false) }
     }
 #undef FS_LAUNCH
     return (int)cudaGetLastError();

@@ -68,6 +68,7 @@ struct ldpc_b200_handle_s {
     RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
     uint32_t* d_pos2 = nullptr; int fs_max_deg = 0;    // staged frame-parallel kernel: edge table with hazard flags
+    uint32_t* d_edge_row = nullptr;                    // ... and (row << 4 | slot) of every edge, for re-expanding compressed messages (debug_state)
     Slot slot[kSlots];
     bool debug = false;
     int8_t* d_dbg_post = nullptr; int8_t* d_dbg_msgs = nullptr; size_t dbg_post_bytes = 0, dbg_msgs_bytes = 0, dbg_frames = 0; int dbg_iters = 0;
@@ -355,7 +356,7 @@ void destroy_impl(ldpc_handle h)
         cudaFree(s.d_queue);
         cudaFree(s.d_llr); cudaFree(s.d_hard); cudaFree(s.d_iters); cudaFree(s.d_V); cudaFree(s.d_MSG); cudaFree(s.d_LLR0);
     }
-    cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2);
+    cudaFree(h->d_steps); cudaFree(h->d_runs); cudaFree(h->d_idx_t); cudaFree(h->d_edge_of); cudaFree(h->d_pos); cudaFree(h->d_pos2); cudaFree(h->d_edge_row);
     cudaFree(h->d_qy); cudaFree(h->d_qq);
     cudaFree(h->d_wf_runs); cudaFree(h->d_wf_vruns); cudaFree(h->d_wf_idx); cudaFree(h->d_wf_cm); cudaFree(h->d_wf_var); cudaFree(h->d_wf_edge_of);
     cudaFree(h->d_dbg_post); cudaFree(h->d_dbg_msgs); cudaFree(h->d_counters); cudaFree(h->d_cptr); cudaFree(h->d_cedge); cudaFree(h->d_oc_rows); cudaFree(h->d_oc_levels);
@@ -618,7 +619,13 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     const int T = (int)((t4 + tq - 1) / tq * tq);
     int rc;
     if ((rc = ensure(h, &s.d_V, &s.v_bytes, (size_t)c.n * T * 4))) return rc;
-    if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, (size_t)c.m * T * 4))) return rc;
+    // staged kernel, compressed messages (kernel_fp.cuh: fp_row_math_c): four words per row and thread instead of one per edge.
+    // reserved[4] bits 16..17: 1 = never, 2 = always (rows of degree <= 8 only); default: see DESIGN.md 3.2b
+    const int cmp_knob = (h->prm.reserved[4] >> 16) & 3;
+    if (cmp_knob == 2 && (h->kernel != 4 || h->fs_max_deg > 8)) return fail(h, LDPC_ERR_UNSUPPORTED, "compressed messages: staged kernel with row degrees <= 8 only");
+    const bool fs_cmp = h->kernel == 4 && h->fs_max_deg <= 8 && cmp_knob == 2;
+    const size_t msg_lines_total = fs_cmp ? (size_t)4 * c.n_checks : (size_t)c.m;
+    if ((rc = ensure(h, &s.d_MSG, &s.msg_bytes, msg_lines_total * T * 4))) return rc;
     s.T = T;
     dim3 tg((unsigned)((frames + 127) / 128), (unsigned)((c.n + 127) / 128));
     // the way in covers every word of the row pitch T (the staged kernel rounds T up to its CTA width and runs all T threads): padding
@@ -657,7 +664,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         f.use_tm = f.use_g4 = 0;
         if (tm_knob != 1 && iters > 0) {
             bool ok = true;
-            for (int i = 0; i < c.nb_deg && ok; i++) ok = make_state_map(&f.tm_msg[i], s.d_MSG, (size_t)c.m, T, nc, c.deg[i]);
+            if (fs_cmp) ok = make_state_map(&f.tm_msg[0], s.d_MSG, msg_lines_total, T, nc, 4);
+            else for (int i = 0; i < c.nb_deg && ok; i++) ok = make_state_map(&f.tm_msg[i], s.d_MSG, (size_t)c.m, T, nc, c.deg[i]);
             if (!ok && tm_knob == 2) return fail(h, LDPC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available or refused the message map");
             f.use_tm = ok ? 1 : 0;
         }
@@ -667,14 +675,15 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
             f.use_g4 = ok ? 1 : 0;
         }
         f.msg_line0 = f.use_g4 ? (f.max_deg + 3) / 4 * 4 : f.max_deg;
-        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.max_deg) * line + FS_P2_BYTES, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
+        f.cmp = fs_cmp ? 1 : 0; f.msg_lines = fs_cmp ? 4 : f.max_deg;
+        const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.msg_lines) * line + FS_P2_BYTES, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob
         f.stages = stages;
         const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + fwd_bytes + stages * stage_bytes;
-        fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? launch_fs_x86 : h->prm.semantics == LDPC_SEM_UNIFORM ? launch_fs_uniform
-                        : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? launch_fs_arm : launch_fs_gpu;
+        fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? (fs_cmp ? launch_fc_x86 : launch_fs_x86) : h->prm.semantics == LDPC_SEM_UNIFORM ? (fs_cmp ? launch_fc_uniform : launch_fs_uniform)
+                        : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? (fs_cmp ? launch_fc_arm : launch_fs_arm) : (fs_cmp ? launch_fc_gpu : launch_fs_gpu);
         f.et = et; f.iters_done = d_it4;
         if (iters > 0) CU_TRY(h, (cudaError_t)fn(h->prm.algo, f, ctas, smem, st));
         else if (d_it4) CU_TRY(h, cudaMemsetAsync(d_it4, 0, (size_t)4 * T, st));
@@ -689,7 +698,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
     h->launches += 3;
     if (d_iters && d_iters != d_it4) CU_TRY(h, cudaMemcpyAsync(d_iters, d_it4, frames, cudaMemcpyDeviceToDevice, st));
     if (want_debug) {
-        fp_debug_state_kernel<<<1024, 256, 0, st>>>(s.d_V, s.d_MSG, h->d_dbg_post, h->d_dbg_msgs, frames, c.n, c.m, T, lo, iters > 0);
+        if (fs_cmp) fc_debug_state_kernel<<<1024, 256, 0, st>>>(s.d_V, s.d_MSG, h->d_edge_row, h->d_dbg_post, h->d_dbg_msgs, frames, c.n, c.m, T, lo, iters > 0);
+        else fp_debug_state_kernel<<<1024, 256, 0, st>>>(s.d_V, s.d_MSG, h->d_dbg_post, h->d_dbg_msgs, frames, c.n, c.m, T, lo, iters > 0);
         CU_TRY(h, cudaGetLastError());
         h->launches += 1;
     }
@@ -928,6 +938,11 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
             CREATE_TRY(cudaMalloc((void**)&h->d_pos2, pos2.size() * sizeof(uint32_t)));
             CREATE_TRY(cudaMemcpy(h->d_pos2, pos2.data(), pos2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             h->kernel = 4; h->fs_max_deg = dmax;
+            std::vector<uint32_t> edge_row((size_t)code->m);
+            { size_t e = 0; uint32_t row = 0;
+              for (int k = 0; k < code->nb_deg; k++) for (int r = 0; r < code->rows[k]; r++, row++) for (int j = 0; j < code->deg[k]; j++) edge_row[e++] = (row << 4) | (uint32_t)j; }
+            CREATE_TRY(cudaMalloc((void**)&h->d_edge_row, edge_row.size() * sizeof(uint32_t)));
+            CREATE_TRY(cudaMemcpy(h->d_edge_row, edge_row.data(), edge_row.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
     }
     if (h->kernel != 2 && !h->levels) h->levels = ldpc_b200_level_schedule(code, nullptr);

@@ -115,14 +115,16 @@ def test_other_codes(built, name):
         assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 4, 4256, 4001])
+@pytest.mark.parametrize("kernel", [0, 1, 4, 4256, 4001, 4002, 4003])
 def test_dvbs2_long_code_frame_parallel(built, kernel):
     """DVB-S2 64800x32400 (a 32 399-deep chain in reference order) against the reference's own x86 decoder (golden fixture):
     plain frame-parallel kernel (1), bulk-copy-staged kernel (4), and whatever the library picks (0 -> 4)."""
     c = Code.load("64800x32400")
     gg = np.load(GOLD / "k4_64800x32400_x86sse.npz")
     # 4256: kernel 4 with 256-consumer CTAs; 4001: kernel 4 with one-dimensional bulk copies only (no tensor map, no gather4)
-    kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4100 else dict(kernel=4, fs_tma=1, fs_g4=1) if kernel == 4001 else dict(kernel=kernel)
+    # 4002 / 4003: kernel 4 on compressed messages (four words per row instead of one per edge), tensor-map / one-dimensional copies
+    kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4100 else dict(kernel=4, fs_tma=1, fs_g4=1) if kernel == 4001 else \
+         dict(kernel=4, fs_cmp=2) if kernel == 4002 else dict(kernel=4, fs_cmp=2, fs_tma=1, fs_g4=1, fs_nc=256) if kernel == 4003 else dict(kernel=kernel)
     r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", **kw)
     assert r["kernel"] == (kw["kernel"] or 4)
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
@@ -204,6 +206,25 @@ def test_staged_kernel_all_semantics(code576, sem, algo):
     assert np.array_equal(g["iters"], o["iters"]) and g["iters"].max() < 50
 
 
+@pytest.mark.parametrize("sem,algo", COMBOS)
+def test_staged_kernel_compressed_messages(code576, sem, algo):
+    """kernel 4 with the check-to-variable messages COMPRESSED (per row and frame: the two magnitudes, which edges get the second one,
+    the signs — kernel_fp.cuh: fp_row_math_c): hard decisions, posteriors AND the re-expanded messages equal the CPU restatement's for
+    every (semantics, algorithm) pair, ring depths, CTA widths, both producer paths, saturating inputs, a ragged tail, early termination
+    with frozen frames and iteration counts."""
+    llr = np.concatenate([awgn_llr(code576, 700, 2.0, 241), stress_llr(code576, 333, 243, full_range=(sem == "GPU_FIXED"))])
+    for iters, stages, nc, tma, g4 in ((1, 0, 128, 2, 2), (10, 0, 128, 2, 2), (3, 2, 128, 2, 2), (3, 15, 128, 2, 2), (10, 0, 256, 2, 2), (3, 2, 256, 1, 1), (2, 9, 256, 1, 2), (10, 0, 128, 1, 1)):
+        g = gpu_decode(code576, llr, iters, algo=algo, semantics=sem, kernel=4, fs_cmp=2, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=g4, want_iters=True)
+        assert g["kernel"] == 4 and (g["iters"] == iters).all()
+        assert_same(g, oracle_decode(code576, g["prm"], llr, iters), f"compressed {sem}/{algo} I{iters} K{stages} NC{nc} tma{tma} g4{g4}")
+    mixed = np.concatenate([awgn_llr(code576, 300, 4.0, 245), awgn_llr(code576, 250, 0.0, 246), awgn_llr(code576, 477, 2.0, 247), stress_llr(code576, 40, 248, full_range=(sem == "GPU_FIXED"))])
+    for iters, stages, nc, tma in ((10, 0, 128, 0), (20, 2, 128, 0), (7, 0, 256, 0), (2, 9, 256, 1), (1, 0, 128, 0)):
+        g = gpu_decode(code576, mixed, iters, algo=algo, semantics=sem, kernel=4, fs_cmp=2, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, early_term=1, want_iters=True)
+        o = oracle_decode(code576, g["prm"], mixed, iters)
+        assert_same(g, o, f"compressed ET {sem}/{algo} I{iters} K{stages} NC{nc}")
+        assert np.array_equal(g["iters"], o["iters"]), f"compressed ET {sem}/{algo} I{iters}: iteration counts"
+
+
 @pytest.mark.parametrize("name,frames", [("576x288", 151552), ("4000x2000", 75776)])
 def test_staged_kernel_stress_against_plain_kernel(built, name, frames):
     """Long-running cross-check of the staged kernel's ordering assumptions (generic-proxy stores -> proxy fence -> mbarrier ->
@@ -215,12 +236,12 @@ def test_staged_kernel_stress_against_plain_kernel(built, name, frames):
     llr = d1.awgn(frames, pkg.sigma_for(1.6, 0.5), seed=77)
     h1, it1 = d1.decode(llr, 40, want_iters=True)
     d1.close()
-    for stages, nc, tma in ((2, 128, 2), (3, 256, 2), (0, 128, 2), (2, 256, 1), (0, 256, 1)):
-        d4 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=4, semantics="ARM_SCALAR", early_term=1, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, chunk_waves=1)
+    for stages, nc, tma, cmp in ((2, 128, 2, 1), (3, 256, 2, 1), (0, 128, 2, 1), (2, 256, 1, 1), (0, 256, 1, 1), (2, 128, 2, 2), (0, 256, 2, 2), (3, 256, 1, 2)):
+        d4 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=4, semantics="ARM_SCALAR", early_term=1, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, fs_cmp=cmp, chunk_waves=1)
         h4, it4 = d4.decode(llr, 40, want_iters=True)
         d4.close()
-        assert np.array_equal(h4, h1), f"{name} K{stages} NC{nc} tma{tma}: {(h4 != h1).any(axis=1).sum()} frames differ"
-        assert np.array_equal(it4, it1), f"{name} K{stages} NC{nc} tma{tma}: iteration counts differ"
+        assert np.array_equal(h4, h1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp}: {(h4 != h1).any(axis=1).sum()} frames differ"
+        assert np.array_equal(it4, it1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp}: iteration counts differ"
     assert it1.min() < 40 and it1.max() == 40
 
 
