@@ -9,7 +9,8 @@ A step = one pass of the hot path over one 65 536-frame batch of synthetic BPSK/
 `e2e`       : the same batch through the blocking C-ABI call ldpc_b200_decode with pinned HOST buffers — H2D, decode, D2H
               inside the timed region (the reference boundary: CGPU_Decoder_OMS_SIMD::decode, gpu_fixed/decoder_oms/...cu:97-149);
               `e2e.host_link` is the pinned-copy rate of THIS box measured in the same process with every rank copying both ways
-              at once, `e2e.ceiling` what that rate allows, `e2e.packed_output` the same call with the bit-packed output format.
+              at once, `e2e.ceiling` what that rate allows, `e2e.packed_output` the same call with the bit-packed output format,
+              `e2e.async_slots` the same buffers through the non-blocking slot API (four batches in flight).
 `roofline`  : HBM roofline of the decode kernel (LLR-in + bits-out bytes per frame, DESIGN.md §Roofline) against MEASURED_PEAKS.json;
 `sm_roofline`: the binding roof for on-chip codes — canonical scalar-int work 18 ops x I x M per frame against
               148 SM x 128 int lanes x clock.
@@ -274,6 +275,26 @@ def time_e2e(torch, ranks, dec, h_llrs, h_out, iters, steps, warmup):
     return s / steps
 
 
+def time_e2e_async(torch, ranks, dec, h_llrs, h_outs, iters, steps, warmup):
+    """The same host-buffer decodes through the NON-blocking slot API (ldpc_b200_decode_async / ldpc_b200_sync): step i goes to stream
+    slot i % 4 as soon as that slot's previous batch has been waited for, so up to four batches are in flight and one batch's copies
+    overlap another's kernel.  Every step still moves its input H2D and its result D2H; wall clock around the loop, max over ranks."""
+    S = len(h_outs)
+    def loop(k):
+        for i in range(k):
+            dec.sync(i % S)                                   # the result of step i - S is in h_outs[i % S] from here on
+            dec.decode_async(i % S, h_llrs[i % len(h_llrs)].array, h_outs[i % S].array, iters)
+        dec.sync()
+    loop(warmup)
+    ranks.barrier()
+    t0 = time.perf_counter()
+    loop(steps)
+    torch.cuda.synchronize()
+    s = ranks.max(time.perf_counter() - t0)
+    ranks.barrier()
+    return s / steps
+
+
 def host_link_probe(torch, ranks, nbytes, chunk, reps=8):
     """Pinned-memory copy rate of this box with EVERY rank copying at once (what e2e is bounded by): H2D alone, D2H alone, both
     directions together, in chunks of the size decode() pipelines.  GB/s per GPU and per direction, the slowest rank's."""
@@ -475,6 +496,15 @@ def main():
     e2e_fps = world * F / e2e_s
     host_fe = int(h_hard.array[:, :k_info].any(axis=1).sum())
 
+    # the non-blocking slot API on the same buffers: four batches in flight (the reference's decode_stream, CGPU_Decoder_MS_SIMD.cu:219-275,
+    # copies synchronously; this one does not)
+    h_outs = [h_hard] + [pkg.PinnedArray((F, n), np.uint8) for _ in range(3)]
+    n_async = max(steps, 12)
+    e2e_async_fps = world * F / time_e2e_async(torch, ranks, dec, h_llr, h_outs, ITERS, n_async, 4)
+    async_ok = all(bool(np.array_equal(h_outs[(n_async - 1 - k) % 4].array, dec.decode(h_llr[(n_async - 1 - k) % 2].array, ITERS))) for k in range(2))
+    for h in h_outs[1:]:
+        h.free()
+
     # the same call with bit-packed output (the new 1-bit-per-bit format: D2H is 8x smaller) — the second, first-class e2e
     decp = pkg.CGPUDecoder(code, nb_frames=F, device=local_rank, out_format=1)
     h_pack = pkg.PinnedArray((F, (n + 7) // 8), np.uint8)
@@ -513,6 +543,9 @@ def main():
                                 "how": f"{world} x min(kernel rate, host_link.both_each_gbs / {n} B): every frame moves {n} B in and {n} B of byte-per-bit decisions out, "
                                        "both directions busy; measured with all ranks copying at once, same process"},
                     "bound": f"host link of this box with {world} rank(s) copying at once: {link['both_each_gbs']:.1f} GB/s per GPU and direction (host_link)",
+                    "async_slots": {"value": e2e_async_fps * k_info / 1e9, "unit": "Gb/s", "frames_per_s": e2e_async_fps, "steps": n_async, "in_flight": 4,
+                                    "frac_of_ceiling": e2e_async_fps / ceil_bytes_fps, "equals_blocking_call": async_ok,
+                                    "api": "ldpc_b200_decode_async + ldpc_b200_sync, one batch per stream slot, same pinned host buffers and bytes per step"},
                     "packed_output": {"value": e2e_packed_fps * k_info / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": F * n, "d2h_bytes_per_step": F * ((n + 7) // 8),
                                       "frames_per_s": e2e_packed_fps, "equals_byte_output": packed_ok,
                                       "ceiling": {"value": ceil_packed_fps * k_info / 1e9, "unit": "Gb/s", "frac_of_ceiling": e2e_packed_fps / ceil_packed_fps,
