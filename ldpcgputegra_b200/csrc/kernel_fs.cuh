@@ -47,6 +47,9 @@ namespace ldpcb200 {
 #define FS_ROW_SHIFT 20
 #define FS_ROW_NONE 15u
 #define FS_ROW_GENERIC 14u
+#define FS_MAXSEG 16                     // consumer-side segments of the row list (see FsArgs::seg_*)
+#define FS_P2_PAD 192                    // words of padding behind pos2: the producers' windows (and the one-row-ahead reads of kernel_fa) run past the last row
+#define FS_STAIR_MIN 32                  // shortest run of staircase rows worth a segment of its own
 
 struct FsArgs {
     uint32_t* V;
@@ -63,6 +66,13 @@ struct FsArgs {
     int use_tm;              // the message lines of a row arrive as ONE 2-D tensor copy (box = nc words x row degree over MSG[m][T])
     int use_g4;              // the posterior lines arrive four at a time (tile::gather4 over V[n][T]); hazard lines come along and are ignored
     int msg_line0;           // first message line of a stage: max_deg, or max_deg rounded up to 4 with gather4 (it writes whole groups of four)
+    // The consumers walk the row list in SEGMENTS: a degree class, cut where a run of STAIRCASE rows begins or ends.  A staircase row has
+    // exactly one hazard edge, at slot D - 2, written by slot D - 1 of the row just before it (the parity chain of DVB-S2 and of every
+    // IRA code: row r holds p[r-1] and p[r] as its last two edges).  Inside such a run the word travels from row to row in a REGISTER
+    // (no forwarding ring, no patch of the stage slot, no proxy fence for it), and row r's own store of p[r] is dropped: row r + 1
+    // overwrites it before anything else can read it.
+    int nseg;
+    int seg_deg[FS_MAXSEG], seg_rows[FS_MAXSEG], seg_cls[FS_MAXSEG], seg_stair[FS_MAXSEG];
     int cmp;                 // compressed messages (the CMP instantiation, rows of degree <= 8): MSG is [4 * rows][T], four words per row and thread
     int msg_lines;           // message lines of a stage: max_deg, or 4 when compressed
     ldpc_params_t prm;
@@ -163,6 +173,41 @@ __device__ __forceinline__ void fs_row(const FsArgs& A, int tid, uint32_t* vt, u
     }
 }
 
+// a STAIRCASE row (FsArgs::seg_*): the hazard word arrives in `carry`, the word the next row needs leaves in it
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP>
+__device__ __forceinline__ void fs_row_stair(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, const uint32_t (&p2)[D], uint32_t stage_s, const RowConsts& K,
+                                             uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool ring_out, bool store_ws, uint32_t& carry,
+                                             uint32_t keep_lo, uint32_t keep_hi)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    constexpr int HS = D - 2, WS = D - 1;
+    constexpr int ML = CMP ? 4 : D;
+    uint32_t wv[D], wm[ML], nv[D], nm[ML];
+#pragma unroll
+    for (int j = 0; j < D; j++) wv[j] = (j == HS) ? carry : lds_u32(stage_s + j * LINE + 4 * tid);
+#pragma unroll
+    for (int j = 0; j < ML; j++) wm[j] = FIRST ? 0x80808080u : lds_u32(stage_s + (A.msg_line0 + j) * LINE + 4 * tid);
+    if constexpr (CMP) fp_row_math_c<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);
+    else fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wv, wm, K, keep_lo, keep_hi, nv, nm);
+    carry = nv[WS];
+    fence_proxy_async_global();
+    __syncwarp();
+    if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (j != WS || store_ws) *word_at(vt, p2[j] & FS_IDX_MASK, T4) = nv[j];
+        if (!CMP) *word_at(mp, (uint32_t)j, T4) = nm[j];
+    }
+    if (CMP) {
+#pragma unroll
+        for (int j = 0; j < ML; j++) *word_at(mp, (uint32_t)j, T4) = nm[j];
+    }
+    if (ring_out) {       // the last FS_FWD rows of a run: the rows after it may forward from them
+#pragma unroll
+        for (int j = 0; j < D; j++) sts_u32(fwd_s + (((q & (FS_FWD - 1)) * (uint32_t)A.max_deg + j) * NC + tid) * 4u, nv[j]);
+    }
+}
+
 // consumer-side ring cursor
 struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 
@@ -170,7 +215,7 @@ struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 // global memory (L1 hit for 3 rows out of 4, L2 otherwise) and used to sit at the head of every row's dependency chain
 // (profiles/r01_ncu_fs_v2.txt: 15 % of the stall samples on the long scoreboard).  pos2 is padded by FS_MAXDEG words so that the
 // read past the last row is harmless; the words fetched across a class boundary are simply dropped.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP>
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP, bool STAIR>
 __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, size_t& rho, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
                                          uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c, uint32_t keep_lo, uint32_t keep_hi)
 {
@@ -178,6 +223,7 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
     uint32_t* const vt = A.V + t;
     uint32_t* mp = A.MSG + ((CMP ? 4 * rho : e) * (size_t)A.T + (size_t)t);
     uint32_t p2[D];
+    uint32_t carry = 0u;
     rho += (size_t)R;
     for (int r = 0; r < R; r++, e += D) {
         mbar_wait(bars + 8 * c.stage, c.phase);
@@ -186,7 +232,16 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
         // row-ahead __ldg sat on the long scoreboard for 14 % of their samples once the producers had stopped being the bottleneck,
         // profiles/r02_ncu_fs_small_v2.txt) — a broadcast shared-memory load behind the barrier they wait on anyway
 #pragma unroll
-        for (int j = 0; j < D; j++) p2[j] = lds_u32(st + FS_P2_OFFSET(A, NC) + 4u * j);
+        for (int j4 = 0; j4 < D; j4 += 4) {              // 16-byte loads: the tail of a stage is 128 bytes, whatever the row's degree
+            const uint4 w = lds_u128(st + FS_P2_OFFSET(A, NC) + 4u * j4);
+            p2[j4] = w.x; if (j4 + 1 < D) p2[j4 + 1] = w.y; if (j4 + 2 < D) p2[j4 + 2] = w.z; if (j4 + 3 < D) p2[j4 + 3] = w.w;
+        }
+        if constexpr (STAIR) {
+            if (r == 0)     // the run's first row: the word comes from the ring (the row before wrote it there) or, at the very start, from memory
+                carry = c.q >= 1 ? lds_u32(fwd_s + ((((c.q - 1u) & (FS_FWD - 1)) * (uint32_t)A.max_deg + (uint32_t)(D - 1)) * NC + tid) * 4u)
+                                 : *word_at(vt, p2[D - 2] & FS_IDX_MASK, T4);
+            fs_row_stair<SEM, ALGO, D, FIRST, Q, NC, ET, CMP>(A, tid, vt, mp, T4, p2, st, K, c.prev_empty, lane, fwd_s, c.q, r + FS_FWD >= R, r + 1 >= R, carry, keep_lo, keep_hi);
+        } else
         fs_row<SEM, ALGO, D, FIRST, Q, NC, ET, CMP>(A, tid, vt, mp, T4, p2, st, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
         mp = word_at(mp, (uint32_t)(CMP ? 4 : D), T4);
         c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
@@ -257,6 +312,112 @@ __device__ __forceinline__ void fs_syndrome_sweep(const FsArgs& A, int tid, int 
     bad_lo &= 0x80008000u; bad_hi &= 0x80008000u;
 }
 
+// ---- producers ---------------------------------------------------------------------------------------------------------------------
+// ET: every iteration but the last is followed by a second pass over the rows for the stop criterion (sweep 1: every line of every row,
+// hazard flags ignored), each pass behind a CTA barrier so that nothing it reads can be stale.  Returns true when the CTA is done.
+template <bool ET>
+__device__ __forceinline__ bool fs_producer_pass_end(int sweeps, int sw)
+{
+    if (ET && sweeps == 2) {
+        if (sw == 0) __syncthreads();                      // the consumers' stores of this iteration are out (they fenced)
+        else if (!__syncthreads_or(0)) return true;        // every frame of the CTA passed: the consumers leave too
+    }
+    return false;
+}
+
+// message side: one tensor copy per row (lane 0 alone) or one bulk copy per message line
+template <int NC, bool ET, bool CMP, bool TM>
+__device__ __forceinline__ void fs_produce_msgs(const FsArgs& A, uint32_t bars, uint32_t ring, uint32_t stage_bytes, int Kst, int t0, int lane)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t dst_line0 = ring + (uint32_t)A.msg_line0 * LINE;
+    for (int it = 0; it < A.iters; it++) {
+        const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
+        for (int sw = 0; sw < sweeps; sw++) {
+            const bool want_msg = it > 0 || sw == 1;
+            int line0 = 0;                                              // the row's first line in MSG (an edge number, or 4 x the row number)
+            for (int c = 0; c < A.nb_deg; c++) {
+                const int R = A.rows[c], ML = CMP ? 4 : A.deg[c];
+                const CUtensorMap* const tm = &A.tm_msg[CMP ? 0 : c];
+                const uint32_t bytes = want_msg ? (uint32_t)ML * LINE : 0u;
+                for (int r = 0; r < R; r++, line0 += ML) {
+                    const uint32_t full = bars + 8 * stage, dst = dst_line0 + (uint32_t)stage * stage_bytes;
+                    // EVERY lane waits for the free slot (one warp instruction either way): a wait by lane 0 alone leaves the warp diverged
+                    // for good, and every __syncwarp / shuffle after it then takes the compiler's WARPSYNC.COLLECTIVE path, 100-250 cycles
+                    // apiece (profiles/r02_ncu_fs_small_v4.txt)
+                    mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);             // slot free (passes at once on the first lap)
+                    if (lane == 0) mbar_arrive_expect_tx(full, bytes);
+                    if (TM) { if (lane == 0 && want_msg) tma_g2s_2d(dst, tm, t0, line0, full); }
+                    else {
+                        __syncwarp();
+                        if (want_msg && lane < ML) bulk_g2s(dst + (uint32_t)lane * LINE, A.MSG + ((size_t)(line0 + lane) * A.T + t0), LINE, full);
+                    }
+                    if (++stage == Kst) { stage = 0; phase ^= 1u; }
+                }
+            }
+            if (fs_producer_pass_end<ET>(sweeps, sw)) return;
+        }
+    }
+}
+
+// posterior side.  The row's edge words (pos2) are the one thing a producer has to LOAD before it can issue anything, and that load
+// queues in the SM's L1TEX path behind every copy already in flight — a whole ring of rows: fetched one row ahead (round 2's first
+// version) its latency WAS the producer's time per row, 578 ns, and with it the time per row of every batch too small to put two CTAs
+// on an SM, whatever the consumers did.  The words now stream through three 32-word windows held across the warp's lanes (W0 = the
+// window the current row starts in, W1, W2 = the next two, loaded 32..64 words = 5..9 rows before their first use); a row's D words
+// are picked out of W0 / W1 with two shuffles.  pos2 is padded by FS_P2_PAD words so the windows may run past the last row.
+// Everything that depends only on the edge words — the gather indices (four shuffles), the line count of the one-dimensional form —
+// is computed BEFORE the wait for a free slot.  The words themselves are left behind the stage's lines for the consumers (with their
+// flags), ordered before lane 0's arrive by the __syncwarp.
+template <int NC, bool ET, bool CMP, bool G4>
+__device__ __forceinline__ void fs_produce_posteriors(const FsArgs& A, uint32_t bars, uint32_t ring, uint32_t stage_bytes, int Kst, int t0, int lane)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t p2_off = FS_P2_OFFSET(A, NC) + 4u * (uint32_t)lane;
+    for (int it = 0; it < A.iters; it++) {
+        const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
+        for (int sw = 0; sw < sweeps; sw++) {
+            const uint32_t* wp = A.pos2 + lane;
+            uint32_t W0 = __ldg(wp), W1 = __ldg(wp + 32), W2 = __ldg(wp + 64);
+            int off = 0;                                                // the current row's first word, relative to W0's first
+            for (int c = 0; c < A.nb_deg; c++) {
+                const int D = A.deg[c], R = A.rows[c];
+                const int groups = (D + 3) >> 2;                        // gather4: lane g < groups fetches edges 4g .. 4g+3 (the last one repeated to fill the group)
+                const int b = 4 * min(lane, groups - 1);
+                const int s0 = b, s1 = min(b + 1, D - 1), s2 = min(b + 2, D - 1), s3 = min(b + 3, D - 1);
+                for (int r = 0; r < R; r++) {
+                    if (off >= 32) { W0 = W1; W1 = W2; wp += 32; W2 = __ldg(wp + 64); off -= 32; }
+                    const int pos = off + lane;
+                    const uint32_t w_lo = __shfl_sync(0xFFFFFFFFu, W0, pos & 31), w_hi = __shfl_sync(0xFFFFFFFFu, W1, pos & 31);
+                    const uint32_t p2_row = lane < D ? (pos < 32 ? w_lo : w_hi) : FS_F_HAZARD;      // with its flags: what the consumers need
+                    off += D;
+                    const bool fetch = lane < D && (sw == 1 || !(p2_row & FS_F_HAZARD));     // one-dimensional form: this lane's line is wanted
+                    const uint32_t idx = p2_row & FS_IDX_MASK;
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                    uint32_t bytes;
+                    if (G4) {
+                        r0 = (int)__shfl_sync(0xFFFFFFFFu, idx, s0); r1 = (int)__shfl_sync(0xFFFFFFFFu, idx, s1);
+                        r2 = (int)__shfl_sync(0xFFFFFFFFu, idx, s2); r3 = (int)__shfl_sync(0xFFFFFFFFu, idx, s3);
+                        bytes = 4u * (uint32_t)groups * LINE;
+                    } else bytes = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, fetch)) * LINE;
+                    const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
+                    mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap); every lane: see fs_produce_msgs
+                    if (lane < D) sts_u32(dst0 + p2_off, p2_row);
+                    __syncwarp();                                        // the edge words, before lane 0's arrive (release)
+                    if (lane == 0) mbar_arrive_expect_tx(full, bytes);
+                    __syncwarp();                                        // the byte count is posted before any copy can complete
+                    if (G4) { if (lane < groups) tma_gather4(dst0 + 4u * (uint32_t)lane * LINE, &A.tm_v, t0, r0, r1, r2, r3, full); }
+                    else if (fetch) bulk_g2s(dst0 + (uint32_t)lane * LINE, A.V + ((size_t)idx * A.T + t0), LINE, full);
+                    if (++stage == Kst) { stage = 0; phase ^= 1u; }
+                }
+            }
+            if (fs_producer_pass_end<ET>(sweeps, sw)) return;
+        }
+    }
+}
+
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
 template <int SEM, int ALGO, int NC, int MAXD, bool ET, bool CMP = false>
@@ -281,67 +442,13 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     if (warp >= NC / 32) {
         // ---------------- two producer warps: warp NC/32 fetches the posterior lines of every row, warp NC/32 + 1 its message lines.
         // Both arrive on the stage's "full" barrier (count 2) with their own byte counts.  (Four producer warps, the edges of a row dealt
-        // out alternately to the two warps of a side, changed nothing — profiles/r02_sweep_fs_pw4.jsonl: the copies are serialised further
-        // down, not in the issuing warp.)
-        const bool msg_side = warp > NC / 32;
-        int stage = 0; uint32_t phase = 0;
-        const int j = lane & 15;
-        const bool mine = lane < 16;
-        // ET: every iteration but the last is followed by a second pass over the rows for the stop criterion (sweep 1: every line of
-        // every row, hazard flags ignored), each pass behind a CTA barrier so that nothing it reads can be stale
-        // The row's edge words are fetched ONE ROW AHEAD (pos2 is padded by FS_MAXDEG words; the words fetched across a class or pass
-        // boundary belong to the row that follows in memory order, which is the next row except at the wrap-around, where they are
-        // re-read): the load used to sit at the head of every row's dependency chain, and at small batches the producers' time per
-        // row IS the kernel's (profiles/r02_ncu_fs_small.txt: the consumers poll the full barrier 67 times per row).
-        const bool idx_lane = !msg_side && mine;
-        for (int it = 0; it < A.iters; it++) {
-            const int sweeps = (ET && it + 1 < A.iters) ? 2 : 1;
-            for (int sw = 0; sw < sweeps; sw++) {
-                size_t e = 0, rho = 0;                               // first edge / number of the row
-                uint32_t p2n = (idx_lane && j < A.deg[0]) ? __ldg(A.pos2 + j) : FS_F_HAZARD;
-                for (int c = 0; c < A.nb_deg; c++) {
-                    const int D = A.deg[c];
-                    for (int r = 0; r < A.rows[c]; r++, e += D, rho++) {
-                        uint32_t p2 = (idx_lane && j < D) ? p2n : FS_F_HAZARD;
-                        {   // next row in memory order: same class, or the first row of the next class
-                            const int Dn = (r + 1 < A.rows[c] || c + 1 >= A.nb_deg) ? D : A.deg[c + 1];
-                            p2n = (idx_lane && j < Dn) ? __ldg(A.pos2 + e + D + j) : FS_F_HAZARD;
-                        }
-                        const uint32_t p2_row = p2;                                         // with its flags: what the consumers need
-                        if (sw == 1 && idx_lane && j < D) p2 &= ~FS_F_HAZARD;
-                        if (lane == 0) mbar_wait(bars + 8 * (Kst + stage), phase ^ 1u);     // slot free (passes at once on the first lap)
-                        __syncwarp();
-                        if (idx_lane && j < D) sts_u32(ring + (uint32_t)stage * stage_bytes + FS_P2_OFFSET(A, NC) + 4u * j, p2_row);   // before lane 0's arrive (release) below
-                        const bool want_msg = it > 0 || sw == 1;
-                        const int groups = (D + 3) >> 2;                       // gather4: lane g < groups fetches edges 4g .. 4g+3 (the last one repeated to fill the group)
-                        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                        if (!msg_side && A.use_g4) {
-                            const int b = 4 * min(lane, groups - 1);
-                            r0 = (int)(__shfl_sync(0xFFFFFFFFu, p2, b) & FS_IDX_MASK); r1 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 1, D - 1)) & FS_IDX_MASK);
-                            r2 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 2, D - 1)) & FS_IDX_MASK); r3 = (int)(__shfl_sync(0xFFFFFFFFu, p2, min(b + 3, D - 1)) & FS_IDX_MASK);
-                        }
-                        const int ML = CMP ? 4 : D;                             // message lines of this row
-                        const size_t ml0 = CMP ? 4 * rho : e;                   // its first line in MSG
-                        const bool go = msg_side ? (mine && want_msg && (A.use_tm ? lane == 0 : j < ML)) : (A.use_g4 ? lane < groups : !(p2 & FS_F_HAZARD));
-                        const uint32_t n_lines = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, go));
-                        const uint32_t full = bars + 8 * stage, dst0 = ring + (uint32_t)stage * stage_bytes;
-                        if (lane == 0) mbar_arrive_expect_tx(full, ((msg_side && A.use_tm) ? (want_msg ? (uint32_t)ML : 0u) : (!msg_side && A.use_g4) ? 4u * n_lines : n_lines) * LINE);
-                        __syncwarp();
-                        if (go) {
-                            if (msg_side && A.use_tm) tma_g2s_2d(dst0 + A.msg_line0 * LINE, &A.tm_msg[CMP ? 0 : c], t0, (int)ml0, full);
-                            else if (msg_side) bulk_g2s(dst0 + (A.msg_line0 + j) * LINE, A.MSG + ((ml0 + j) * A.T + t0), LINE, full);
-                            else if (A.use_g4) tma_gather4(dst0 + 4u * (uint32_t)lane * LINE, &A.tm_v, t0, r0, r1, r2, r3, full);
-                            else bulk_g2s(dst0 + j * LINE, A.V + ((size_t)(p2 & FS_IDX_MASK) * A.T + t0), LINE, full);
-                        }
-                        if (++stage == Kst) { stage = 0; phase ^= 1u; }
-                    }
-                }
-                if (ET && sweeps == 2) {
-                    if (sw == 0) __syncthreads();                      // the consumers' stores of this iteration are out (they fenced)
-                    else if (!__syncthreads_or(0)) return;             // every frame of the CTA passed: the consumers leave too
-                }
-            }
-        }
+        // out alternately to the two warps of a side, changed nothing — profiles/r02_sweep_fs_pw4.jsonl.)
+        // Each side is its own tight loop, specialised on the copy form: with one consumer warp per scheduler a batch is only as fast as
+        // the SLOWER producer walks the row list, and the first version's common loop (run-time side / form flags, class tables re-read
+        // from constant memory every row, a ballot to count lines) was a serial chain of ~130 instructions = 1136 cycles per row —
+        // exactly the 578 ns per row every small batch ran at, whatever the ring depth (profiles/r02_ncu_fs_small_v3.txt).
+        if (warp > NC / 32) { if (A.use_tm) fs_produce_msgs<NC, ET, CMP, true>(A, bars, ring, stage_bytes, Kst, t0, lane); else fs_produce_msgs<NC, ET, CMP, false>(A, bars, ring, stage_bytes, Kst, t0, lane); }
+        else                { if (A.use_g4) fs_produce_posteriors<NC, ET, CMP, true>(A, bars, ring, stage_bytes, Kst, t0, lane); else fs_produce_posteriors<NC, ET, CMP, false>(A, bars, ring, stage_bytes, Kst, t0, lane); }
         return;
     }
 
@@ -355,12 +462,14 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
     int it = 0;
     for (; it < A.iters; it++) {
         size_t e = 0, rho = 0;
-        for (int c = 0; c < A.nb_deg; c++) {
-            const int D = A.deg[c], R = A.rows[c];
+        for (int sg = 0; sg < A.nseg; sg++) {
+            const int D = A.seg_deg[sg], R = A.seg_rows[sg], c = A.seg_cls[sg];
+            const bool stair = A.seg_stair[sg] != 0;
             const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
             // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
             K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
-#define FS_GO(DD, FI, QQ) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET, CMP>(A, tid, t, e, rho, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
+#define FS_GO_(DD, FI, QQ, ST) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET, CMP, ST>(A, tid, t, e, rho, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
+#define FS_GO(DD, FI, QQ) do { if constexpr (DD >= 6 && DD <= 8) { if (stair) FS_GO_(DD, FI, QQ, true); else FS_GO_(DD, FI, QQ, false); } else FS_GO_(DD, FI, QQ, false); } while (0)
 #define FS_CASE(DD)                                                                          \
     case DD:                                                                                 \
         if constexpr (DD <= MAXD) {                                                          \
@@ -371,6 +480,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
             switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
 #undef FS_CASE
 #undef FS_GO
+#undef FS_GO_
         }
         if (ET && it + 1 < A.iters) {
             __threadfence();                           // once per iteration: this iteration's stores are performed ...

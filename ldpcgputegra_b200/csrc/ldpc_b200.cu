@@ -68,6 +68,7 @@ struct ldpc_b200_handle_s {
     RpStep* d_steps = nullptr; RpRun* d_runs = nullptr; uint16_t* d_idx_t = nullptr; uint32_t* d_edge_of = nullptr;
     uint32_t* d_pos = nullptr;
     uint32_t* d_pos2 = nullptr; int fs_max_deg = 0;    // staged frame-parallel kernel: edge table with hazard flags
+    int fs_nseg = 0, fs_seg_deg[FS_MAXSEG] = {}, fs_seg_rows[FS_MAXSEG] = {}, fs_seg_cls[FS_MAXSEG] = {}, fs_seg_stair[FS_MAXSEG] = {};   // consumer-side segments (kernel_fs.cuh: FsArgs::seg_*)
     uint32_t* d_edge_row = nullptr;                    // ... and (row << 4 | slot) of every edge, for re-expanding compressed messages (debug_state)
     Slot slot[kSlots];
     bool debug = false;
@@ -675,6 +676,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
             f.use_g4 = ok ? 1 : 0;
         }
         f.msg_line0 = f.use_g4 ? (f.max_deg + 3) / 4 * 4 : f.max_deg;
+        f.nseg = h->fs_nseg;
+        for (int i = 0; i < h->fs_nseg; i++) { f.seg_deg[i] = h->fs_seg_deg[i]; f.seg_rows[i] = h->fs_seg_rows[i]; f.seg_cls[i] = h->fs_seg_cls[i]; f.seg_stair[i] = h->fs_seg_stair[i]; }
         f.cmp = fs_cmp ? 1 : 0; f.msg_lines = fs_cmp ? 4 : f.max_deg;
         const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.msg_lines) * line + FS_P2_BYTES, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
         int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
@@ -907,9 +910,10 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
         if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs row degrees 3..10 and >= 128 rows"); }
         if (ok && params->kernel != 1) {
             // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
-            std::vector<uint32_t> pos2((size_t)code->m + FS_MAXDEG, 0u);      // padded: the consumers fetch one row ahead
+            std::vector<uint32_t> pos2((size_t)code->m + FS_P2_PAD, 0u);      // padded: the consumers fetch one row ahead
             std::vector<long> last((size_t)code->n, -(long)(1 << 30));
             std::vector<int> last_slot((size_t)code->n, 0);
+            std::vector<uint8_t> stair_row((size_t)code->n_checks, 0);      // exactly one hazard edge: slot D-2, written by slot D-1 of the row before
             for (int lap = 0; lap < 2; lap++) {
                 long q = (long)lap * code->n_checks; size_t e = 0;
                 for (int k = 0; k < code->nb_deg; k++)
@@ -932,12 +936,38 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
                             pos2[e0] |= hs << FS_ROW_SHIFT;
                             pos2[e0 + 1] |= (uint32_t)wslot << FS_ROW_SHIFT;
                             pos2[e0 + 2] |= (uint32_t)(hback > 0 ? (hback - 1) & 3 : 0) << FS_ROW_SHIFT;
+                            const int D = code->deg[k];
+                            stair_row[(size_t)(q - code->n_checks)] = (nhaz == 1 && hslot == D - 2 && wslot == D - 1 && hback == 1 && D >= 6 && D <= 8) ? 1 : 0;
                         }
                     }
             }
             CREATE_TRY(cudaMalloc((void**)&h->d_pos2, pos2.size() * sizeof(uint32_t)));
             CREATE_TRY(cudaMemcpy(h->d_pos2, pos2.data(), pos2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             h->kernel = 4; h->fs_max_deg = dmax;
+            // consumer-side segments: every degree class, cut around its runs of >= FS_STAIR_MIN staircase rows (reserved[4] bit 18: none)
+            {
+                struct Seg { int deg, rows, cls, stair; };
+                std::vector<Seg> segs;
+                const bool no_stair = (params->reserved[4] >> 18) & 1;
+                size_t row = 0;
+                for (int k = 0; k < code->nb_deg; k++) {
+                    const size_t r0 = row, r1 = row + (size_t)code->rows[k];
+                    size_t a = r0;
+                    while (a < r1) {
+                        size_t b = a;
+                        const bool st = !no_stair && stair_row[a];
+                        while (b < r1 && (bool)(!no_stair && stair_row[b]) == st) b++;
+                        const bool keep = st && b - a >= FS_STAIR_MIN;
+                        if (!segs.empty() && segs.back().cls == k && !segs.back().stair && !keep) segs.back().rows += (int)(b - a);
+                        else segs.push_back({ code->deg[k], (int)(b - a), k, keep ? 1 : 0 });
+                        a = b;
+                    }
+                    row = r1;
+                }
+                if (segs.size() > FS_MAXSEG) { segs.clear(); for (int k = 0; k < code->nb_deg; k++) segs.push_back({ code->deg[k], code->rows[k], k, 0 }); }
+                h->fs_nseg = (int)segs.size();
+                for (size_t i = 0; i < segs.size(); i++) { h->fs_seg_deg[i] = segs[i].deg; h->fs_seg_rows[i] = segs[i].rows; h->fs_seg_cls[i] = segs[i].cls; h->fs_seg_stair[i] = segs[i].stair; }
+            }
             std::vector<uint32_t> edge_row((size_t)code->m);
             { size_t e = 0; uint32_t row = 0;
               for (int k = 0; k < code->nb_deg; k++) for (int r = 0; r < code->rows[k]; r++, row++) for (int j = 0; j < code->deg[k]; j++) edge_row[e++] = (row << 4) | (uint32_t)j; }
