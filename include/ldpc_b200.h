@@ -121,7 +121,8 @@ typedef struct {
                                    | message lines through a TMA tensor map (bits 12..13: 1 = never, 2 = always)
                                    | posterior lines through tile::gather4 (bits 14..15, likewise)
                                    | compressed messages, four words per row instead of one per edge (bits 16..17: 2 = on, rows of degree <= 8;
-                                     bit-exact, 2/3 of the state, measured slightly SLOWER: off unless asked for — DESIGN.md 3.2b) */
+                                     bit-exact, 2/3 of the state, measured slightly SLOWER: off unless asked for — DESIGN.md 3.2b)
+                                   | bit 18: no register-carried staircase runs | bits 19..20: paired staircase rows (1 = never, 2 = always) */
 } ldpc_params_t;
 
 typedef struct ldpc_b200_handle_s* ldpc_handle;

@@ -226,6 +226,9 @@ def default_params(**kw) -> ParamsT:
         if k == "fs_nostair":     # staged kernel: no register-carried staircase runs (every row through the forwarding ring, as in round 1): A/B experiments
             p.reserved[4] = (p.reserved[4] & ~(1 << 18)) | (int(bool(v)) << 18)
             continue
+        if k == "fs_pipe2":       # staged kernel: paired staircase rows (small-batch instantiation): 0 = library's choice, 1 = never, 2 = always (A/B experiments)
+            p.reserved[4] = (p.reserved[4] & ~(3 << 19)) | (int(v) << 19)
+            continue
         if k == "fs_cmp":         # staged kernel: compressed messages (four words per row instead of one per edge): 0 = library's choice, 1 = never, 2 = always
             p.reserved[4] = (p.reserved[4] & ~(3 << 16)) | (int(v) << 16)
             continue

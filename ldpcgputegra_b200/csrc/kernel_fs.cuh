@@ -7,7 +7,7 @@
 // each, NC = 128 | 256 consumer threads) into a K-stage ring with cp.async.bulk (TMA, non-tensor form) completing on an mbarrier
 // per stage; consumers read their word from the stage, do the row, store the results straight to HBM, and hand the stage back.
 // Memory-level parallelism is then K rows x 14 lines x NC*4 B per CTA whatever the number of resident threads.  Measured
-// (DESIGN.md 3.2b): DVB-S2 20.5 Gb/s = 0.89 of the measured HBM peak on algorithmic bytes at a batch that fills every SM alike.
+// (DESIGN.md 3.2b): DVB-S2 21.6 Gb/s = 0.94 of the measured HBM peak on algorithmic bytes at a batch that fills every SM alike.
 // (The reference re-reads both arrays through a per-row __syncthreads pair: code/gpu_fixed/decoder_oms/cuda/CUDA_OMS_SIMD.cu:141-187.)
 //
 // Staleness.  A line prefetched for row q was read up to K rows early, so it is wrong if one of the K rows before q wrote the
@@ -73,6 +73,7 @@ struct FsArgs {
     // overwrites it before anything else can read it.
     int nseg;
     int seg_deg[FS_MAXSEG], seg_rows[FS_MAXSEG], seg_cls[FS_MAXSEG], seg_stair[FS_MAXSEG];
+    int pipe2;               // the paired-row instantiation (PIPE2): the host asks for it when a CTA has an SM to itself and the code has staircase runs
     int cmp;                 // compressed messages (the CMP instantiation, rows of degree <= 8): MSG is [4 * rows][T], four words per row and thread
     int msg_lines;           // message lines of a stage: max_deg, or 4 when compressed
     ldpc_params_t prm;
@@ -208,6 +209,54 @@ __device__ __forceinline__ void fs_row_stair(const FsArgs& A, int tid, uint32_t*
     }
 }
 
+// TWO consecutive staircase rows in one basic block (the small-batch instantiation, PIPE2): with one consumer warp per scheduler a row
+// is a serial chain of ~400 instructions, and everything of row B that does not depend on row A — six of its seven posterior words,
+// all its messages, their unpacking, saturation, magnitudes and most of the min search — can issue between A's dependent
+// instructions once both rows' words are in registers.  Neither row is one of a run's last FS_FWD (no ring writes, no store of
+// slot D - 1).  A's stage is handed back together with the stage of the row before it: its words are in registers by then.
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP>
+__device__ __forceinline__ void fs_row_stair2(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, const uint32_t (&p2a)[D], const uint32_t (&p2b)[D],
+                                              uint32_t st_a, uint32_t st_b, const RowConsts& K, uint32_t prev_empty, uint32_t empty_a, int lane, uint32_t& carry,
+                                              uint32_t keep_lo, uint32_t keep_hi)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    constexpr int HS = D - 2, WS = D - 1;
+    constexpr int ML = CMP ? 4 : D;
+    uint32_t wva[D], wma[ML], nva[D], nma[ML], wvb[D], wmb[ML], nvb[D], nmb[ML];
+#pragma unroll
+    for (int j = 0; j < D; j++) wva[j] = (j == HS) ? carry : lds_u32(st_a + j * LINE + 4 * tid);
+#pragma unroll
+    for (int j = 0; j < ML; j++) wma[j] = FIRST ? 0x80808080u : lds_u32(st_a + (A.msg_line0 + j) * LINE + 4 * tid);
+#pragma unroll
+    for (int j = 0; j < D; j++) wvb[j] = (j == HS) ? 0u : lds_u32(st_b + j * LINE + 4 * tid);
+#pragma unroll
+    for (int j = 0; j < ML; j++) wmb[j] = FIRST ? 0x80808080u : lds_u32(st_b + (A.msg_line0 + j) * LINE + 4 * tid);
+    if constexpr (CMP) fp_row_math_c<SEM, ALGO, D, FIRST, ET, Q>(wva, wma, K, keep_lo, keep_hi, nva, nma);
+    else fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wva, wma, K, keep_lo, keep_hi, nva, nma);
+    wvb[HS] = nva[WS];
+    if constexpr (CMP) fp_row_math_c<SEM, ALGO, D, FIRST, ET, Q>(wvb, wmb, K, keep_lo, keep_hi, nvb, nmb);
+    else fp_row_math<SEM, ALGO, D, FIRST, ET, Q>(wvb, wmb, K, keep_lo, keep_hi, nvb, nmb);
+    carry = nvb[WS];
+    fence_proxy_async_global();
+    __syncwarp();
+    if (lane == 0) { if (prev_empty) mbar_arrive(prev_empty); mbar_arrive(empty_a); }
+    uint32_t* const mpb = word_at(mp, (uint32_t)ML, T4);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (j != WS) *word_at(vt, p2a[j] & FS_IDX_MASK, T4) = nva[j];
+        if (!CMP) *word_at(mp, (uint32_t)j, T4) = nma[j];
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (j != WS) *word_at(vt, p2b[j] & FS_IDX_MASK, T4) = nvb[j];
+        if (!CMP) *word_at(mpb, (uint32_t)j, T4) = nmb[j];
+    }
+    if (CMP) {
+#pragma unroll
+        for (int j = 0; j < ML; j++) { *word_at(mp, (uint32_t)j, T4) = nma[j]; *word_at(mpb, (uint32_t)j, T4) = nmb[j]; }
+    }
+}
+
 // consumer-side ring cursor
 struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 
@@ -215,7 +264,7 @@ struct FsCursor { int stage; uint32_t phase, prev_empty, q; };
 // global memory (L1 hit for 3 rows out of 4, L2 otherwise) and used to sit at the head of every row's dependency chain
 // (profiles/r01_ncu_fs_v2.txt: 15 % of the stall samples on the long scoreboard).  pos2 is padded by FS_MAXDEG words so that the
 // read past the last row is harmless; the words fetched across a class boundary are simply dropped.
-template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP, bool STAIR>
+template <int SEM, int ALGO, int D, bool FIRST, bool Q, int NC, bool ET, bool CMP, bool STAIR, bool PIPE2>
 __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t& e, size_t& rho, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
                                          uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c, uint32_t keep_lo, uint32_t keep_hi)
 {
@@ -228,6 +277,28 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
     for (int r = 0; r < R; r++, e += D) {
         mbar_wait(bars + 8 * c.stage, c.phase);
         const uint32_t st = ring + (uint32_t)c.stage * stage_bytes;
+        if constexpr (STAIR && PIPE2) {
+            if (r >= 1 && r + 1 + FS_FWD < R) {       // rows r and r + 1 as a pair (row 0 sets up the carry, the last FS_FWD rows feed the ring)
+                const int stage_b = c.stage + 1 == Kst ? 0 : c.stage + 1;
+                const uint32_t phase_b = c.stage + 1 == Kst ? c.phase ^ 1u : c.phase;
+                mbar_wait(bars + 8 * stage_b, phase_b);
+                const uint32_t st_b = ring + (uint32_t)stage_b * stage_bytes;
+                uint32_t p2b[D];
+#pragma unroll
+                for (int j4 = 0; j4 < D; j4 += 4) {
+                    const uint4 w = lds_u128(st + FS_P2_OFFSET(A, NC) + 4u * j4), wb = lds_u128(st_b + FS_P2_OFFSET(A, NC) + 4u * j4);
+                    p2[j4] = w.x; if (j4 + 1 < D) p2[j4 + 1] = w.y; if (j4 + 2 < D) p2[j4 + 2] = w.z; if (j4 + 3 < D) p2[j4 + 3] = w.w;
+                    p2b[j4] = wb.x; if (j4 + 1 < D) p2b[j4 + 1] = wb.y; if (j4 + 2 < D) p2b[j4 + 2] = wb.z; if (j4 + 3 < D) p2b[j4 + 3] = wb.w;
+                }
+                fs_row_stair2<SEM, ALGO, D, FIRST, Q, NC, ET, CMP>(A, tid, vt, mp, T4, p2, p2b, st, st_b, K, c.prev_empty, bars + 8 * (Kst + c.stage), lane, carry, keep_lo, keep_hi);
+                mp = word_at(mp, (uint32_t)(2 * (CMP ? 4 : D)), T4);
+                c.prev_empty = bars + 8 * (Kst + stage_b); c.q += 2;
+                c.stage = stage_b; c.phase = phase_b;
+                if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
+                r++; e += D;
+                continue;
+            }
+        }
         // the row's edge words: written behind the stage's lines by the producer that fetched them (round 2: the consumers' own
         // row-ahead __ldg sat on the long scoreboard for 14 % of their samples once the producers had stopped being the bottleneck,
         // profiles/r02_ncu_fs_small_v2.txt) — a broadcast shared-memory load behind the barrier they wait on anyway
@@ -420,8 +491,8 @@ __device__ __forceinline__ void fs_produce_posteriors(const FsArgs& A, uint32_t 
 
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
-template <int SEM, int ALGO, int NC, int MAXD, bool ET, bool CMP = false>
-__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
+template <int SEM, int ALGO, int NC, int MAXD, bool ET, bool CMP = false, bool PIPE2 = false>
+__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, PIPE2 ? 1 : (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];
@@ -468,7 +539,7 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (MAXD <= 8 ? 512 : 3
             const bool quirk = SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS && c >= 1;
             // the reference's OMS kernel forgets the 31-clamp for the second degree class in its peeled first iteration (CUDA_OMS_SIMD.cu:113-114)
             K.msg_c = (SEM == LDPC_SEM_GPU_FIXED && ALGO == LDPC_ALGO_OMS && it == 0 && c >= 1) ? K.one : K.msg;
-#define FS_GO_(DD, FI, QQ, ST) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET, CMP, ST>(A, tid, t, e, rho, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
+#define FS_GO_(DD, FI, QQ, ST) fs_class<SEM, ALGO, DD, FI, QQ, NC, ET, CMP, ST, PIPE2>(A, tid, t, e, rho, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi)
 #define FS_GO(DD, FI, QQ) do { if constexpr (DD >= 6 && DD <= 8) { if (stair) FS_GO_(DD, FI, QQ, true); else FS_GO_(DD, FI, QQ, false); } else FS_GO_(DD, FI, QQ, false); } while (0)
 #define FS_CASE(DD)                                                                          \
     case DD:                                                                                 \

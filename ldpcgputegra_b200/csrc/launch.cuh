@@ -60,6 +60,16 @@ static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
       if (e != cudaSuccess) return (int)e;                                                                                                      \
       fs_decode_kernel<SEM, ALGO, NCV, MD, ETV, CMP><<<blocks, NCV + FS_PRODUCER_THREADS, smem, st>>>(a); }
     if (CMP && a.max_deg > 8) return (int)cudaErrorInvalidValue;        // compressed rows carry 8 edge bits per frame
+    // one CTA per SM and staircase runs in the code: the paired-row instantiation (kernel_fs.cuh: fs_row_stair2), no register cap
+    if (!CMP && a.pipe2 && a.nc == 128 && a.max_deg <= 8) {
+#define FS_LAUNCH2(ETV)                                                                                                                       \
+    { cudaError_t e = cudaFuncSetAttribute(fs_decode_kernel<SEM, ALGO, 128, 8, ETV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return (int)e;                                                                                                      \
+      fs_decode_kernel<SEM, ALGO, 128, 8, ETV, false, true><<<blocks, 128 + FS_PRODUCER_THREADS, smem, st>>>(a); }
+        if constexpr (!CMP) { if (a.et) FS_LAUNCH2(true) else FS_LAUNCH2(false) }
+#undef FS_LAUNCH2
+        return (int)cudaGetLastError();
+    }
     // CTA width x widest row body x early termination.  The kernel's registers are those of its widest body, and the two producer
     // warps get the same allocation as the consumers: 256 consumers per CTA keep 16 consumer warps on an SM where 128 keep 12
     // (DESIGN.md 3.2b).  320 consumers capped at 80 registers (20 consumer warps) were measured 3 % SLOWER at a balanced batch and

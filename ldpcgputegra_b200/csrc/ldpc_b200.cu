@@ -684,6 +684,13 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob
         f.stages = stages;
+        {   // paired staircase rows: only where at most two CTAs share an SM (124-146 registers), reserved[4] bits 19..20: 1 = never, 2 = always
+            const int p2_knob = (h->prm.reserved[4] >> 19) & 3;
+            bool any_stair = false;
+            for (int i = 0; i < h->fs_nseg; i++) any_stair = any_stair || h->fs_seg_stair[i];
+            f.pipe2 = (any_stair && !fs_cmp && nc == 128 && f.max_deg <= 8 && p2_knob != 1 && (p2_knob == 2 || ctas <= 2 * h->sms) && stages >= 4) ? 1 : 0;     // the pair holds three stages
+
+        }
         const size_t smem = (size_t)((16 * stages + 127) / 128 * 128) + fwd_bytes + stages * stage_bytes;
         fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? (fs_cmp ? launch_fc_x86 : launch_fs_x86) : h->prm.semantics == LDPC_SEM_UNIFORM ? (fs_cmp ? launch_fc_uniform : launch_fs_uniform)
                         : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? (fs_cmp ? launch_fc_arm : launch_fs_arm) : (fs_cmp ? launch_fc_gpu : launch_fs_gpu);

@@ -115,7 +115,7 @@ def test_other_codes(built, name):
         assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 4, 4256, 4001, 4002, 4003])
+@pytest.mark.parametrize("kernel", [0, 1, 4, 4256, 4001, 4002, 4003, 4004, 4005])
 def test_dvbs2_long_code_frame_parallel(built, kernel):
     """DVB-S2 64800x32400 (a 32 399-deep chain in reference order) against the reference's own x86 decoder (golden fixture):
     plain frame-parallel kernel (1), bulk-copy-staged kernel (4), and whatever the library picks (0 -> 4)."""
@@ -124,7 +124,8 @@ def test_dvbs2_long_code_frame_parallel(built, kernel):
     # 4256: kernel 4 with 256-consumer CTAs; 4001: kernel 4 with one-dimensional bulk copies only (no tensor map, no gather4)
     # 4002 / 4003: kernel 4 on compressed messages (four words per row instead of one per edge), tensor-map / one-dimensional copies
     kw = dict(kernel=4, fs_nc=kernel - 4000) if kernel > 4100 else dict(kernel=4, fs_tma=1, fs_g4=1) if kernel == 4001 else \
-         dict(kernel=4, fs_cmp=2) if kernel == 4002 else dict(kernel=4, fs_cmp=2, fs_tma=1, fs_g4=1, fs_nc=256) if kernel == 4003 else dict(kernel=kernel)
+         dict(kernel=4, fs_cmp=2) if kernel == 4002 else dict(kernel=4, fs_cmp=2, fs_tma=1, fs_g4=1, fs_nc=256) if kernel == 4003 else \
+         dict(kernel=4, fs_pipe2=1) if kernel == 4004 else dict(kernel=4, fs_nostair=1) if kernel == 4005 else dict(kernel=kernel)     # 4004: staircase rows one by one; 4005: no staircase runs
     r = gpu_decode(c, gg["llr"], 10, algo="OMS", semantics="X86_SSE", **kw)
     assert r["kernel"] == (kw["kernel"] or 4)
     assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg["OMS_1_10_hard"])
@@ -223,6 +224,60 @@ def test_staged_kernel_compressed_messages(code576, sem, algo):
         o = oracle_decode(code576, g["prm"], mixed, iters)
         assert_same(g, o, f"compressed ET {sem}/{algo} I{iters} K{stages} NC{nc}")
         assert np.array_equal(g["iters"], o["iters"]), f"compressed ET {sem}/{algo} I{iters}: iteration counts"
+
+
+def _ira_code(d0, r0, d1, r1, k_sys, seed):
+    """A synthetic IRA code: two degree classes, every row = (d - 2) systematic columns + the parity staircase p[r-1], p[r] as its last
+    two edges (DVB-S2's structure), the systematic columns laid out so that no column repeats within 17 rows — except in a handful of
+    rows, which get a second hazard on purpose and cut the staircase runs into pieces of different lengths (one of them shorter than
+    the 32 rows a run needs to become a segment of its own)."""
+    rng = np.random.default_rng(seed)
+    cuts = {100, 101, 300, r0 + 120, r0 + 380, r0 + 420, r0 + 440}
+    rows = [(d0, r) for r in range(r0)] + [(d1, r0 + r) for r in range(r1)]
+    stream, guard = [], 17 * max(d0, d1)                   # random permutations of the systematic columns, no repeat within `guard` entries
+    while len(stream) < (r0 + r1) * max(d0, d1):
+        perm = rng.permutation(k_sys).tolist()
+        if not set(perm[:guard]) & set(stream[-guard:]):
+            stream += perm
+    pos, cursor = [], 0
+    for d, r in rows:
+        take = d - 2 if r else d - 1                         # row 0 has no p[-1]: one more systematic column
+        cols = stream[cursor:cursor + take]
+        cursor += take
+        if r in cuts:
+            cols[int(rng.integers(d - 2))] = int(prev[int(rng.integers(len(prev)))])     # a systematic column of the row before: second hazard
+        pos += cols + ([k_sys + r - 1, k_sys + r] if r else [k_sys])
+        prev = cols
+    return Code(k_sys + r0 + r1, r0 + r1, [d0, d1], [r0, r1], np.asarray(pos, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("d0,d1", [(8, 7), (7, 6)])
+def test_staged_kernel_staircase_runs(built, d0, d1):
+    """The register-carried staircase runs of the staged kernel (kernel_fs.cuh: fs_row_stair, fs_row_stair2) on synthetic IRA codes whose
+    runs are cut at random places, cross a degree-class boundary and wrap around the iteration: single rows, paired rows, neither,
+    ring depths that switch the pairing off, compressed messages, every semantics family, early termination with frozen frames —
+    hard decisions, posteriors, messages and iteration counts equal the CPU restatement's."""
+    c = _ira_code(d0, 520, d1, 731, 1999, 7 * d0 + d1)
+    llr = np.concatenate([awgn_llr(c, 260, 1.5, 31), stress_llr(c, 63, 32)])
+    variants = [dict(), dict(fs_pipe2=1), dict(fs_pipe2=2), dict(fs_nostair=1), dict(fs_pipe2=2, fs_stages=4), dict(fs_pipe2=2, fs_stages=15), dict(fs_stages=3),
+                dict(fs_cmp=2), dict(fs_nc=256), dict(fs_tma=1, fs_g4=1, fs_pipe2=2)]
+    for sem, algo in (("X86_SSE", "OMS"), ("X86_SSE", "NMS"), ("GPU_FIXED", "2NMS"), ("ARM_SCALAR", "OMS")):
+        prm = None
+        for kw in variants:
+            g = gpu_decode(c, llr, 6, algo=algo, semantics=sem, kernel=4, **kw)
+            assert g["kernel"] == 4
+            if prm is None:
+                prm, o = g["prm"], oracle_decode(c, g["prm"], llr, 6)
+            assert_same(g, o, f"staircase {d0}/{d1} {sem}/{algo} {kw}")
+    mixed = np.concatenate([awgn_llr(c, 150, 4.0, 33), awgn_llr(c, 120, 0.5, 34), awgn_llr(c, 90, 2.0, 35)])
+    oe = None
+    for kw in (dict(), dict(fs_pipe2=1), dict(fs_nostair=1), dict(fs_cmp=2), dict(fs_pipe2=2, fs_stages=5)):
+        g = gpu_decode(c, mixed, 15, algo="OMS", semantics="ARM_SCALAR", kernel=4, early_term=1, want_iters=True, **kw)
+        if oe is None:
+            oe = oracle_decode(c, g["prm"], mixed, 15)
+        assert_same(g, oe, f"staircase ET {d0}/{d1} {kw}")
+        assert np.array_equal(g["iters"], oe["iters"]), kw
+    assert oe["iters"].min() < 15
 
 
 @pytest.mark.parametrize("name,frames", [("576x288", 151552), ("4000x2000", 75776)])
