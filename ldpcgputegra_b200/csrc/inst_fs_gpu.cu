@@ -5,13 +5,16 @@
 
 namespace ldpcb200 {
 
+int launch_fs_gpu_ms(const FsArgs& args, int blocks, size_t smem, cudaStream_t st);
+int launch_fs_gpu_nms(const FsArgs& args, int blocks, size_t smem, cudaStream_t st);
+
 int launch_fs_gpu(int algo, const FsArgs& args, int blocks, size_t smem, cudaStream_t st)
 {
     switch (algo) {
-    case LDPC_ALGO_MS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_MS>(args, blocks, smem, st);
+    case LDPC_ALGO_MS: return launch_fs_gpu_ms(args, blocks, smem, st);            // inst_fs_gpu_ms.cu (build parallelism)
     case LDPC_ALGO_OMS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_OMS>(args, blocks, smem, st);
     case LDPC_ALGO_NMS:
-    case LDPC_ALGO_2NMS: return do_fs<LDPC_SEM_GPU_FIXED, LDPC_ALGO_NMS>(args, blocks, smem, st);
+    case LDPC_ALGO_2NMS: return launch_fs_gpu_nms(args, blocks, smem, st);         // inst_fs_gpu_nms.cu
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -544,8 +544,10 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, PIPE2 ? 1 : (MAXD <=
 #define FS_CASE(DD)                                                                          \
     case DD:                                                                                 \
         if constexpr (DD <= MAXD) {                                                          \
+        if constexpr (SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS) {                    \
         if (it == 0) { if (quirk) FS_GO(DD, true, true); else FS_GO(DD, true, false); }      \
         else         { if (quirk) FS_GO(DD, false, true); else FS_GO(DD, false, false); }    \
+        } else { if (it == 0) FS_GO(DD, true, false); else FS_GO(DD, false, false); }        \
         }                                                                                    \
         break;
             switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
