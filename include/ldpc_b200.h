@@ -110,7 +110,7 @@ typedef struct {
     int32_t out_format;   /* ldpc_out_format_t                             */
     int32_t kernel;       /* 0 = auto; 1 = frame-parallel (HBM-resident state); 2 = row-parallel on-chip (short codes);
                              3 = generic engine (fp32 arithmetic: int16 / float / flooding, and int8 layered as a cross-check);
-                             4 = frame-parallel with the state staged through shared memory by cp.async.bulk (long codes);
+                             4 = frame-parallel with the state staged through shared memory by cp.async.bulk / tensor-map copies (long codes; row degrees 3..32);
                              5 = generic engine with the state on chip, a CTA owns F frames (int16 / float / flooding on short codes);
                              6 = generic engine with the state on chip, ONE WARP PER FRAME and a global work queue (the same modes; chosen
                                  when >= 8 frames fit per SM and the schedule fills the lanes: flooding, or layered with wide levels) */

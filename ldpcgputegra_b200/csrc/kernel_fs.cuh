@@ -37,11 +37,14 @@ namespace ldpcb200 {
 #define FS_P2_OFFSET(A, NC) ((uint32_t)((A).msg_line0 + (A).msg_lines) * (uint32_t)(NC) * 4u)
 #define FS_LINE (FS_CONSUMERS * 4)       // bytes per staged line at NC = 128
 #define FS_MAXDEG 10                     // 1200x600, the gpu_fixed tree's default code (matrix/code.h:1), has rows of degree 9
+#define FS_GEN_MAXDEG 32                 // rows up to this degree run through the two-pass row body (fs_row_generic): DVB-S2 rates 8/9 and 9/10 have rows of 27 and 30
 #define FS_HAZARD 16                     // hazard window in rows = the largest ring depth the host may choose
 #define FS_FWD 4                         // rows whose outputs stay in the forwarding ring
 #define FS_F_HAZARD 0x80000000u          // pos2 flags: not prefetched (written within the hazard window) ...
 #define FS_F_FWD    0x40000000u          // ... and the writer is at most FS_FWD rows back: bits 29..28 = rows back - 1, bits 27..24 = its edge slot
 #define FS_IDX_MASK 0x000FFFFFu
+// Tables with a row degree above FS_MAXDEG carry no row summary and a 5-bit writer slot in bits 27..23 instead (FS_GEN_SLOT).
+#define FS_GEN_SLOT(p2) (((p2) >> 23) & 31u)
 // Row summary in bits 23..20 of the row's first three words (every row has >= 3 edges): word 0 = slot of the row's ONLY hazard edge
 // when that edge can be forwarded (14 = some other hazard pattern, 15 = no hazard), word 1 = the writer's slot, word 2 = rows back - 1.
 #define FS_ROW_SHIFT 20
@@ -320,6 +323,88 @@ __device__ __forceinline__ void fs_class(const FsArgs& A, int tid, int t, size_t
     }
 }
 
+// ---- rows of ANY degree up to FS_GEN_MAXDEG (the MAXD = FS_GEN_MAXDEG instantiation): two passes over the stage, nothing of the row in
+// registers — the min search first, then every edge recomputed from the staged words with the row's two constants (the structure of
+// fp_row_generic in kernel_fp.cuh, with shared memory where that one reads HBM twice).  Hazard words (forwarding ring or memory) are
+// written into their stage slot during pass 1 so that pass 2 finds them there.
+template <int SEM, int ALGO, bool FIRST, bool Q, int NC, bool ET>
+__device__ __noinline__ void fs_row_generic(const FsArgs& A, int tid, uint32_t* vt, uint32_t* mp, uint32_t T4, int D, uint32_t stage_s, const RowConsts& K,
+                                            uint32_t prev_empty, int lane, uint32_t fwd_s, uint32_t q, bool fwd_ok, uint32_t keep_lo, uint32_t keep_hi)
+{
+    constexpr uint32_t LINE = NC * 4u;
+    const h2 inv256 = h2_const(1.0f / 256.0f), half = h2_const(0.5f);
+    const uint32_t p2s = stage_s + FS_P2_OFFSET(A, NC), vs = stage_s + 4u * (uint32_t)tid, ms = vs + (uint32_t)A.msg_line0 * LINE;
+    RowState s[2]; row_begin(s[0], K); row_begin(s[1], K);
+    bool patched = false;
+    for (int j = 0; j < D; j++) {
+        const uint32_t p2 = lds_u32(p2s + 4u * j);
+        uint32_t wv;
+        if (p2 & FS_F_HAZARD) {                                    // warp-uniform: the flags belong to the row
+            if ((p2 & FS_F_FWD) && fwd_ok) {
+                const uint32_t back = ((p2 >> 28) & 3u) + 1u;
+                wv = lds_u32(fwd_s + ((((q - back) & (FS_FWD - 1)) * (uint32_t)A.max_deg + FS_GEN_SLOT(p2)) * NC + tid) * 4u);
+            } else wv = *word_at(vt, p2 & FS_IDX_MASK, T4);
+            sts_u32(vs + j * LINE, wv);
+            patched = true;
+        } else wv = lds_u32(vs + j * LINE);
+        const uint32_t wm = FIRST ? 0x80808080u : lds_u32(ms + j * LINE);
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const h2 wU = g ? bytes23_to_w(wv, K.c64) : bytes01_to_w(wv, K.c64);
+            const h2 wM = g ? bytes23_to_w(wm, K.c64) : bytes01_to_w(wm, K.c64);
+            const h2 xu = __hmin2(__hfma2_sat(wU, inv256, __hfma2(wM, __hneg2(inv256), half)), K.top);
+            pass1_edge<SEM, ALGO, Q>(s[g], xu, K);
+        }
+    }
+    if (patched) fence_proxy_async_shared();                       // generic-proxy writes of stage slots, before the copy engine refills them (see fs_row)
+    RowOut o[2]; row_finish<SEM, ALGO>(s[0], D, K, K.msg_c, o[0]); row_finish<SEM, ALGO>(s[1], D, K, K.msg_c, o[1]);
+    fence_proxy_async_global();                                    // the previous rows' stores, before any later bulk copy of the same lines
+    __syncwarp();
+    if (lane == 0 && prev_empty) mbar_arrive(prev_empty);
+    const uint32_t keep = __byte_perm(keep_lo, keep_hi, 0x6420);
+    const uint32_t fwd_row = fwd_s + (((q & (FS_FWD - 1)) * (uint32_t)A.max_deg) * NC + tid) * 4u;
+    for (int j = 0; j < D; j++) {
+        const uint32_t p2 = lds_u32(p2s + 4u * j);
+        const uint32_t wv = lds_u32(vs + j * LINE);
+        const uint32_t wm = FIRST ? 0x80808080u : lds_u32(ms + j * LINE);
+        uint32_t ov[2], om[2];
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const h2 wU = g ? bytes23_to_w(wv, K.c64) : bytes01_to_w(wv, K.c64);
+            const h2 wM = g ? bytes23_to_w(wm, K.c64) : bytes01_to_w(wm, K.c64);
+            const h2 xu = __hmin2(__hfma2_sat(wU, inv256, __hfma2(wM, __hneg2(inv256), half)), K.top);
+            const h2 a = magnitude<SEM, ALGO, Q>(signed_contrib(xu, K), K);
+            h2 msg, unew;
+            pass2_edge<SEM>(xu, a, o[g], K, msg, unew);
+            ov[g] = q_to_w(unew, 0.0f); om[g] = q_to_w(msg, 128.0f);
+        }
+        uint32_t nv = pack_bytes(ov[0], ov[1]), nm = pack_bytes(om[0], om[1]);
+        if (ET) {   // frozen frames keep their state
+            nv = (wv & keep) | (nv & ~keep);
+            nm = FIRST ? nm : ((wm & keep) | (nm & ~keep));
+        }
+        *word_at(vt, p2 & FS_IDX_MASK, T4) = nv;
+        *word_at(mp, (uint32_t)j, T4) = nm;
+        sts_u32(fwd_row + (uint32_t)j * LINE, nv);
+    }
+}
+
+template <int SEM, int ALGO, bool FIRST, bool Q, int NC, bool ET>
+__device__ __forceinline__ void fs_class_generic(const FsArgs& A, int tid, int t, size_t& e, int D, int R, const RowConsts& K, int lane, uint32_t bars, uint32_t ring,
+                                                 uint32_t stage_bytes, uint32_t fwd_s, int Kst, FsCursor& c, uint32_t keep_lo, uint32_t keep_hi)
+{
+    const uint32_t T4 = 4u * (uint32_t)A.T;
+    uint32_t* const vt = A.V + t;
+    uint32_t* mp = A.MSG + (e * (size_t)A.T + (size_t)t);
+    for (int r = 0; r < R; r++, e += D) {
+        mbar_wait(bars + 8 * c.stage, c.phase);
+        fs_row_generic<SEM, ALGO, FIRST, Q, NC, ET>(A, tid, vt, mp, T4, D, ring + (uint32_t)c.stage * stage_bytes, K, c.prev_empty, lane, fwd_s, c.q, c.q >= FS_FWD, keep_lo, keep_hi);
+        mp = word_at(mp, (uint32_t)D, T4);
+        c.prev_empty = bars + 8 * (Kst + c.stage); c.q++;
+        if (++c.stage == Kst) { c.stage = 0; c.phase ^= 1u; }
+    }
+}
+
 // Stop criterion, consumer side: one more pass over the row list through the same ring — the producers fetch EVERY line of a row
 // this time (nothing is written, so nothing can be stale once the update pass has drained) — and per row the parity of (x > 0),
 // x = sat(v - m) with the updated messages (ref: code/ldpc_decoder_arm/CDecoder/OMS/CDecoder_OMS_fixed_x86.cpp:150-178; the same
@@ -492,7 +577,7 @@ __device__ __forceinline__ void fs_produce_posteriors(const FsArgs& A, uint32_t 
 // MAXD: the largest row degree this instantiation carries (8 | FS_MAXDEG) — a kernel's register allocation is that of its widest row
 // body, and DVB-S2 (degrees 7 and 6) should not pay for the degree-10 body of 1200x600
 template <int SEM, int ALGO, int NC, int MAXD, bool ET, bool CMP = false, bool PIPE2 = false>
-__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, PIPE2 ? 1 : (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
+__global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, (PIPE2 || MAXD > FS_MAXDEG) ? 1 : (MAXD <= 8 ? 512 : 384) / NC) fs_decode_kernel(const __grid_constant__ FsArgs A)
 {
     constexpr uint32_t LINE = NC * 4u;
     extern __shared__ __align__(128) unsigned char fs_smem[];
@@ -550,6 +635,19 @@ __global__ void __launch_bounds__(NC + FS_PRODUCER_THREADS, PIPE2 ? 1 : (MAXD <=
         } else { if (it == 0) FS_GO(DD, true, false); else FS_GO(DD, false, false); }        \
         }                                                                                    \
         break;
+            if constexpr (MAXD > FS_MAXDEG) {       // the two-pass row body for every row, whatever its degree
+                static_assert(!CMP && !PIPE2, "the generic row body has neither compressed messages nor paired rows");
+                if constexpr (SEM == LDPC_SEM_X86_SSE && ALGO == LDPC_ALGO_OMS) {
+                    if (it == 0) { if (quirk) fs_class_generic<SEM, ALGO, true, true, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi);
+                                   else fs_class_generic<SEM, ALGO, true, false, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi); }
+                    else         { if (quirk) fs_class_generic<SEM, ALGO, false, true, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi);
+                                   else fs_class_generic<SEM, ALGO, false, false, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi); }
+                } else {
+                    if (it == 0) fs_class_generic<SEM, ALGO, true, false, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi);
+                    else fs_class_generic<SEM, ALGO, false, false, NC, ET>(A, tid, t, e, D, R, K, lane, bars, ring, stage_bytes, fwd_s, Kst, cur, keep_lo, keep_hi);
+                }
+                (void)stair; (void)rho;
+            } else
             switch (D) { FS_CASE(3) FS_CASE(4) FS_CASE(5) FS_CASE(6) FS_CASE(7) FS_CASE(8) FS_CASE(9) FS_CASE(10) }
 #undef FS_CASE
 #undef FS_GO

@@ -76,10 +76,10 @@ static int do_fs(const FsArgs& a, int blocks, size_t smem, cudaStream_t st)
     // the degree-10 body needs 120 registers (one wide CTA per SM, never a win): neither is instantiated.
     if (a.et) {
         if (a.nc == 256 && a.max_deg <= 8) FS_LAUNCH(256, 8, true)
-        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, true) else if constexpr (!CMP) FS_LAUNCH(128, FS_MAXDEG, true) }
+        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, true) else if constexpr (!CMP) { if (a.max_deg <= FS_MAXDEG) FS_LAUNCH(128, FS_MAXDEG, true) else FS_LAUNCH(128, FS_GEN_MAXDEG, true) } }
     } else {
         if (a.nc == 256 && a.max_deg <= 8) FS_LAUNCH(256, 8, false)
-        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, false) else if constexpr (!CMP) FS_LAUNCH(128, FS_MAXDEG, false) }
+        else { if (a.max_deg <= 8) FS_LAUNCH(128, 8, false) else if constexpr (!CMP) { if (a.max_deg <= FS_MAXDEG) FS_LAUNCH(128, FS_MAXDEG, false) else FS_LAUNCH(128, FS_GEN_MAXDEG, false) } }
     }
 #undef FS_LAUNCH
     return (int)cudaGetLastError();

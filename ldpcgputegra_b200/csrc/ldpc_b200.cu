@@ -654,7 +654,8 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         const int nc = fs_nc;
         f.nc = nc;
         // ring depth: as deep as shared memory allows for the CTAs that will share an SM, at most the hazard window
-        const int ctas = T / nc, per_sm = std::min(nc == 128 ? 4 : 2, std::max(1, (ctas + h->sms - 1) / h->sms));
+        const int ctas = T / nc;
+        int per_sm = std::min(nc == 128 ? 4 : 2, std::max(1, (ctas + h->sms - 1) / h->sms));
         // message lines as one 2-D tensor copy per row (TMA tensor map) instead of D one-dimensional bulk copies, posterior lines four
         // at a time (tile::gather4): the copy engine serves requests one after the other (~46 cycles each), which is what bounds a
         // batch too small to put 16 consumer warps on an SM.  reserved[4] bits 12..13 (message map) and 14..15 (gather4): 1 = never,
@@ -680,7 +681,9 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         for (int i = 0; i < h->fs_nseg; i++) { f.seg_deg[i] = h->fs_seg_deg[i]; f.seg_rows[i] = h->fs_seg_rows[i]; f.seg_cls[i] = h->fs_seg_cls[i]; f.seg_stair[i] = h->fs_seg_stair[i]; }
         f.cmp = fs_cmp ? 1 : 0; f.msg_lines = fs_cmp ? 4 : f.max_deg;
         const size_t line = (size_t)nc * 4, stage_bytes = (size_t)(f.msg_line0 + f.msg_lines) * line + FS_P2_BYTES, fwd_bytes = (size_t)FS_FWD * f.max_deg * line;
-        int stages = (int)(((size_t)(220 * 1024) / per_sm - fwd_bytes - 256) / stage_bytes);
+        auto stages_for = [&](int ps) { return (int)(((long)(220 * 1024) / ps - (long)fwd_bytes - 256) / (long)stage_bytes); };
+        while (per_sm > 1 && stages_for(per_sm) < 4) per_sm--;          // wide rows make wide stages: fewer CTAs per SM rather than a ring too shallow to hide anything
+        int stages = stages_for(per_sm);
         stages = std::max(2, std::min(stages, FS_HAZARD - 1));   // a stage is handed back one row late (fs_row)
         if ((h->prm.reserved[4] & 255) >= 2 && (h->prm.reserved[4] & 255) < FS_HAZARD) stages = h->prm.reserved[4] & 255;     // experiment knob
         f.stages = stages;
@@ -913,9 +916,13 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
     if (h->kernel == 1) {
         bool ok = code->n_checks >= 8 * FS_HAZARD;
         int dmax = 0;
-        for (int i = 0; i < code->nb_deg; i++) { ok = ok && code->deg[i] >= 3 && code->deg[i] <= FS_MAXDEG && code->n <= (int)FS_IDX_MASK; dmax = std::max(dmax, code->deg[i]); }
-        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs row degrees 3..10 and >= 128 rows"); }
-        if (ok && params->kernel != 1) {
+        for (int i = 0; i < code->nb_deg; i++) { ok = ok && code->deg[i] >= 3 && code->deg[i] <= FS_GEN_MAXDEG && code->n <= (int)FS_IDX_MASK; dmax = std::max(dmax, code->deg[i]); }
+        if (params->kernel == 4 && !ok) { destroy_impl(h); return fail(nullptr, LDPC_ERR_UNSUPPORTED, "staged frame-parallel kernel: needs row degrees 3..32 and >= 128 rows"); }
+        // rows wider than FS_MAXDEG run through the two-pass row body (fs_row_generic): no row summary, 5-bit writer slots
+        const bool wide = dmax > FS_MAXDEG;
+        // wide rows: the staged kernel runs one CTA per SM on them (wide stages) and a two-pass row body — 2.6x the plain kernel at 64 Ki
+        // DVB-S2 rate-8/9 frames, level with it at 256 Ki (profiles/r02_sweep_fs_wide.jsonl): chosen below 256 Ki frames of capacity, or on request
+        if (ok && params->kernel != 1 && (!wide || params->kernel == 4 || h->max_frames < 262144)) {
             // hazard flags: an edge whose variable was touched by one of the FS_HAZARD previous rows (cyclic over the iteration boundary)
             std::vector<uint32_t> pos2((size_t)code->m + FS_P2_PAD, 0u);      // padded: the consumers fetch one row ahead
             std::vector<long> last((size_t)code->n, -(long)(1 << 30));
@@ -933,12 +940,12 @@ int ldpc_b200_create(ldpc_handle* out, const ldpc_code_t* code, const ldpc_param
                             if (lap == 1) {
                                 uint32_t w = v;
                                 if (back <= FS_HAZARD) { w |= FS_F_HAZARD; nhaz++; hslot = j; wslot = last_slot[v]; hback = back; fwd = back <= FS_FWD; }
-                                if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << 24);
+                                if (back <= FS_FWD) w |= FS_F_FWD | ((uint32_t)(back - 1) << 28) | ((uint32_t)last_slot[v] << (wide ? 23 : 24));
                                 pos2[e] = w;
                             }
                             last[v] = q; last_slot[v] = j;
                         }
-                        if (lap == 1) {     // row summary (kernel_fs.cuh: FS_ROW_SHIFT)
+                        if (lap == 1 && !wide) {     // row summary (kernel_fs.cuh: FS_ROW_SHIFT)
                             const uint32_t hs = nhaz == 0 ? FS_ROW_NONE : (nhaz == 1 && fwd) ? (uint32_t)hslot : FS_ROW_GENERIC;
                             pos2[e0] |= hs << FS_ROW_SHIFT;
                             pos2[e0 + 1] |= (uint32_t)wslot << FS_ROW_SHIFT;

@@ -108,6 +108,15 @@ def test_other_codes(built, name):
             oe = oracle_decode(c, g4e["prm"], llr, 12)
             assert_same(g4e, oe, f"{name} {sem}/{algo} kernel 4 early termination")
             assert np.array_equal(g4e["iters"], oe["iters"])
+        elif c.n_checks >= 128 and max(c.deg) <= 32 and min(c.deg) >= 3:   # rows wider than 10: the staged kernel's two-pass row body, on request
+            for kw in (dict(), dict(fs_tma=1, fs_g4=1), dict(fs_stages=2)):
+                g4 = gpu_decode(c, llr, 5, algo=algo, semantics=sem, kernel=4, **kw)
+                assert g4["kernel"] == 4
+                assert_same(g4, o, f"{name} {sem}/{algo} kernel 4 (wide rows) {kw}")
+            g4e = gpu_decode(c, llr, 12, algo=algo, semantics=sem, kernel=4, early_term=1, want_iters=True)
+            oe = oracle_decode(c, g4e["prm"], llr, 12)
+            assert_same(g4e, oe, f"{name} {sem}/{algo} kernel 4 (wide rows) early termination")
+            assert np.array_equal(g4e["iters"], oe["iters"])
     gold = GOLD / f"k4_{name}_x86sse.npz"
     if gold.exists():
         gg = np.load(gold)
@@ -143,13 +152,14 @@ def test_dvbs2_high_rate_tables(built, name):
     gg = np.load(GOLD / f"k4_{name}_x86sse.npz")
     for algo, param in (("OMS", 1), ("NMS", 29)):
         key = f"{algo}_{param}_10"
-        for kernel in (0, 1):
+        for kernel in (0, 1, 4):          # 4: the staged kernel's two-pass row body for rows wider than 10
             r = gpu_decode(c, gg["llr"], 10, algo=algo, semantics="X86_SSE", offset=param, factor_q5=param, kernel=kernel)
             assert np.array_equal(np.packbits(r["hard"], axis=1, bitorder="little"), gg[key + "_hard"]), (key, kernel)
             assert [hashlib.sha256(r["post"].tobytes()).hexdigest(), hashlib.sha256(r["msgs"].tobytes()).hexdigest()] == list(gg[key + "_sha"]), (key, kernel, r["kernel"])
     # GPU_FIXED semantics and early termination on the same table against the CPU restatement (a handful of frames: the oracle is scalar)
     llr = gg["llr"][4:10]
-    for kw in (dict(algo="OMS", semantics="GPU_FIXED"), dict(algo="OMS", semantics="ARM_SCALAR", early_term=1)):
+    for kw in (dict(algo="OMS", semantics="GPU_FIXED"), dict(algo="OMS", semantics="ARM_SCALAR", early_term=1), dict(algo="2NMS", semantics="GPU_FIXED", kernel=4),
+               dict(algo="OMS", semantics="ARM_SCALAR", early_term=1, kernel=4), dict(algo="NMS", semantics="UNIFORM", early_term=1, kernel=4, fs_tma=1, fs_g4=1)):
         g = gpu_decode(c, llr, 12, want_iters=True, **kw)
         o = oracle_decode(c, g["prm"], llr, 12)
         assert_same(g, o, f"{name} {kw}")
