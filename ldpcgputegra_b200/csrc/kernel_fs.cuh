@@ -22,6 +22,12 @@
 // The common pattern — one forwardable hazard edge per row — is summarised per row (FS_ROW_SHIFT) and served by copying the ring word
 // into the stage slot.  Early termination (template parameter ET) adds a second, read-only pass over the ring per iteration for the
 // per-frame stop criterion (fs_syndrome_sweep) and a CTA-wide exit.
+// Round 2: the message lines of a row arrive as one 2-D tensor-map copy and the posterior lines four at a time through
+// tile::gather4; the producers are two separate tight loops whose warps stay CONVERGED (every lane waits for the free slot — a wait by
+// lane 0 alone left every later shuffle / __syncwarp on the compiler's divergent path and WAS the time per row of every small batch);
+// runs of staircase rows carry their hazard word in a register (fs_row_stair), in pairs sharing one basic block where a CTA has room
+// for the registers (fs_row_stair2, the PIPE2 instantiation); rows of degree 11..32 take a two-pass body (fs_row_generic); the messages
+// may be stored compressed, four words per row (CMP: bit-exact, fewer bytes, more instructions, not faster).
 // Roofline: HBM, 4*M bytes per frame-iteration as for kernel_fp.
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only: the encoder is looked up at run time, ldpc_b200.cu)
