@@ -158,7 +158,10 @@ enum { LDPC_INFO_KERNEL = 0,            /* which decode kernel the handle select
        LDPC_INFO_FRAMES_PER_CTA = 3,
        LDPC_INFO_LAUNCHES = 4,          /* kernels launched by this handle so far (for bench.py's gpu_launches)     */
        LDPC_INFO_STREAM_SLOTS = 5,
-       LDPC_INFO_DEVICE = 6 };
+       LDPC_INFO_DEVICE = 6,
+       LDPC_INFO_FS_STAIR_ROWS = 7,     /* staged kernel: rows of H inside register-carried staircase runs (0: none)  */
+       LDPC_INFO_FS_VARIANT = 8 };      /* staged kernel, last launch: rows per consumer group (1 | 2) | 16 if the two-pass
+                                           wide-row body ran | 32 if the messages were compressed | 256 x consumers per CTA */
 
 /* LLR quantisation (ref: CFastFixConversion::generate code/x86/CFixPointConversion/CFastFixConversion.cpp:55-65;
  * GPU twin LDPC_Convert_Float_LLR_to_8b_Fixed_Point code/gpu_fixed/decoder_template/GPU_Scheduled_functions.cu:54-64):

@@ -31,7 +31,7 @@ SCHED = {"LAYERED": 0, "FLOODING": 1}
 DTYPE = {"I8": 0, "I16": 1, "F32": 2}
 NP_DTYPE = {0: np.int8, 1: np.int16, 2: np.float32}
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_IO, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-INFO_KERNEL, INFO_LEVELS, INFO_SMEM_BYTES, INFO_FRAMES_PER_CTA, INFO_LAUNCHES, INFO_STREAM_SLOTS, INFO_DEVICE = range(7)
+INFO_KERNEL, INFO_LEVELS, INFO_SMEM_BYTES, INFO_FRAMES_PER_CTA, INFO_LAUNCHES, INFO_STREAM_SLOTS, INFO_DEVICE, INFO_FS_STAIR_ROWS, INFO_FS_VARIANT = range(9)
 
 
 class LdpcError(RuntimeError):

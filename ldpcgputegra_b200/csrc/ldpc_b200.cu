@@ -69,6 +69,7 @@ struct ldpc_b200_handle_s {
     uint32_t* d_pos = nullptr;
     uint32_t* d_pos2 = nullptr; int fs_max_deg = 0;    // staged frame-parallel kernel: edge table with hazard flags
     int fs_nseg = 0, fs_seg_deg[FS_MAXSEG] = {}, fs_seg_rows[FS_MAXSEG] = {}, fs_seg_cls[FS_MAXSEG] = {}, fs_seg_stair[FS_MAXSEG] = {};   // consumer-side segments (kernel_fs.cuh: FsArgs::seg_*)
+    int64_t fs_last_variant = 0;                       // LDPC_INFO_FS_VARIANT
     uint32_t* d_edge_row = nullptr;                    // ... and (row << 4 | slot) of every edge, for re-expanding compressed messages (debug_state)
     Slot slot[kSlots];
     bool debug = false;
@@ -698,6 +699,7 @@ int launch_decode(ldpc_handle h, Slot& s, const int8_t* d_llr, uint8_t* d_hard, 
         fs_launch_fn fn = h->prm.semantics == LDPC_SEM_X86_SSE ? (fs_cmp ? launch_fc_x86 : launch_fs_x86) : h->prm.semantics == LDPC_SEM_UNIFORM ? (fs_cmp ? launch_fc_uniform : launch_fs_uniform)
                         : h->prm.semantics == LDPC_SEM_ARM_SCALAR ? (fs_cmp ? launch_fc_arm : launch_fs_arm) : (fs_cmp ? launch_fc_gpu : launch_fs_gpu);
         f.et = et; f.iters_done = d_it4;
+        h->fs_last_variant = (f.pipe2 ? 2 : 1) | (f.max_deg > FS_MAXDEG ? 16 : 0) | (fs_cmp ? 32 : 0) | 256 * (int64_t)nc;
         if (iters > 0) CU_TRY(h, (cudaError_t)fn(h->prm.algo, f, ctas, smem, st));
         else if (d_it4) CU_TRY(h, cudaMemsetAsync(d_it4, 0, (size_t)4 * T, st));
     } else {
@@ -1022,6 +1024,8 @@ int ldpc_b200_get_info(ldpc_handle h, int what, int64_t* value)
     case LDPC_INFO_LAUNCHES: *value = h->launches; break;
     case LDPC_INFO_STREAM_SLOTS: *value = kSlots; break;
     case LDPC_INFO_DEVICE: *value = h->device; break;
+    case LDPC_INFO_FS_STAIR_ROWS: { int64_t n = 0; for (int i = 0; i < h->fs_nseg; i++) if (h->fs_seg_stair[i]) n += h->fs_seg_rows[i]; *value = n; break; }
+    case LDPC_INFO_FS_VARIANT: *value = h->fs_last_variant; break;
     default: return fail(h, LDPC_ERR_INVALID, "unknown info key");
     }
     return LDPC_OK;

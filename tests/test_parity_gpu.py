@@ -182,7 +182,17 @@ def test_dvbs2_early_termination_staged_vs_plain_vs_oracle(built):
     assert o["iters"].min() < 25 and o["iters"].max() == 25          # some frames stop early, the 0.5 dB ones never do
     auto = pkg.CGPUDecoder(c, nb_frames=16, device=0, early_term=1)
     assert auto.info(pkg.INFO_KERNEL) == 4
+    # the fast paths are really the ones that run: 32 398 of the 32 400 rows sit in one register-carried staircase run, and a batch this
+    # small is decoded by the paired-row instantiation with 128 consumers per CTA
+    assert auto.info(pkg.INFO_FS_STAIR_ROWS) == 32398
+    auto.decode(llr[:16], 2)
+    assert auto.info(pkg.INFO_FS_VARIANT) == 2 + 256 * 128
     auto.close()
+    wide = pkg.CGPUDecoder(Code.load("64800x7200"), nb_frames=16, device=0)
+    assert wide.info(pkg.INFO_KERNEL) == 4 and wide.info(pkg.INFO_FS_STAIR_ROWS) == 0
+    wide.decode(np.zeros((16, 64800), dtype=np.int8), 1)
+    assert wide.info(pkg.INFO_FS_VARIANT) == 1 + 16 + 256 * 128
+    wide.close()
 
 
 @pytest.mark.parametrize("sem,algo", COMBOS)
