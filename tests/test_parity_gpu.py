@@ -300,7 +300,7 @@ def test_staged_kernel_staircase_runs(built, d0, d1):
     assert oe["iters"].min() < 15
 
 
-@pytest.mark.parametrize("name,frames", [("576x288", 151552), ("4000x2000", 75776)])
+@pytest.mark.parametrize("name,frames", [("576x288", 151552), ("4000x2000", 75776), ("64800x32400", 9472)])
 def test_staged_kernel_stress_against_plain_kernel(built, name, frames):
     """Long-running cross-check of the staged kernel's ordering assumptions (generic-proxy stores -> proxy fence -> mbarrier ->
     bulk / tensor-map copies of the same lines, the forwarded word written into a stage slot the copy engine refills): many
@@ -311,12 +311,16 @@ def test_staged_kernel_stress_against_plain_kernel(built, name, frames):
     llr = d1.awgn(frames, pkg.sigma_for(1.6, 0.5), seed=77)
     h1, it1 = d1.decode(llr, 40, want_iters=True)
     d1.close()
-    for stages, nc, tma, cmp in ((2, 128, 2, 1), (3, 256, 2, 1), (0, 128, 2, 1), (2, 256, 1, 1), (0, 256, 1, 1), (2, 128, 2, 2), (0, 256, 2, 2), (3, 256, 1, 2)):
-        d4 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=4, semantics="ARM_SCALAR", early_term=1, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, fs_cmp=cmp, chunk_waves=1)
+    variants = ((2, 128, 2, 1, 0), (3, 256, 2, 1, 0), (0, 128, 2, 1, 0), (2, 256, 1, 1, 0), (0, 256, 1, 1, 0), (2, 128, 2, 2, 0), (0, 256, 2, 2, 0), (3, 256, 1, 2, 0))
+    if name == "64800x32400":       # DVB-S2: the staircase runs — single rows, pairs (ring depths 4 and 15), neither, compressed — for 40 iterations each
+        variants = ((0, 128, 2, 1, 2), (4, 128, 2, 1, 2), (15, 128, 1, 1, 2), (0, 128, 2, 1, 1), (0, 256, 2, 1, 1), (3, 128, 2, 1, 0), (0, 128, 2, 2, 0))
+    for stages, nc, tma, cmp, pipe in variants:
+        d4 = pkg.CGPUDecoder(c, nb_frames=frames, kernel=4, semantics="ARM_SCALAR", early_term=1, fs_stages=stages, fs_nc=nc, fs_tma=tma, fs_g4=tma, fs_cmp=cmp, fs_pipe2=pipe,
+                             fs_nostair=int(name == "64800x32400" and stages == 3), chunk_waves=1)
         h4, it4 = d4.decode(llr, 40, want_iters=True)
         d4.close()
-        assert np.array_equal(h4, h1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp}: {(h4 != h1).any(axis=1).sum()} frames differ"
-        assert np.array_equal(it4, it1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp}: iteration counts differ"
+        assert np.array_equal(h4, h1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp} pipe{pipe}: {(h4 != h1).any(axis=1).sum()} frames differ"
+        assert np.array_equal(it4, it1), f"{name} K{stages} NC{nc} tma{tma} cmp{cmp} pipe{pipe}: iteration counts differ"
     assert it1.min() < 40 and it1.max() == 40
 
 
